@@ -1,0 +1,404 @@
+#!/usr/bin/env python3
+"""bench.py - EM link-updates/s of the MMSBM hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4]
+
+A "step" is one EM iteration (Model.make_iteration, TIP.py:984-1043) over one rank's link shard.
+Workload at every N (weak scaling): BASELINE config 2 per GPU - 6,000 genes, K=10, the fold-1
+training split of 1M triplets = 800,000 links per rank; with N>1 the links are sharded over ranks
+(N x 800,000 links in total) and every iteration carries one NCCL allreduce of the statistics.
+`--workload cfg4` runs BASELINE config 4 instead (1e8 links in total, strong scaling).
+
+Prints ONE JSON line on rank 0.  `value` = link-updates/s with inputs resident in HBM; `e2e` = the
+same through the host-buffer C-ABI call (H2D of rows/theta/p and D2H of theta/p inside the timed
+region); `roofline` is against the fp64 FMA peak MEASURED in this run (the kernel is DFMA bound,
+6*K^3 flops per link-update); `cpu_baseline` is the CPython oracle port on this box's cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_GENES, K_GROUPS = 6000, 10
+L_PER_GPU = 800_000
+CFG4_LINKS = 100_000_000
+METRIC = "EM link-updates/sec at K=10"
+UNIT = "link-updates/s"
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.002):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:  # noqa: BLE001
+            self.nv, self.err = None, str(exc)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self) -> dict:
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                    "note": "no NVML samples" if self.nv else "NVML unavailable"}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------- CPU legs
+def _cpu_worker(args):
+    """One core: literal-loop oracle EM step (the CPython reference restated) on its own link sample."""
+    seed, n_links, P, K = args
+    import numpy as np
+    from oracle import mmsbm_oracle as orc
+    rng = np.random.default_rng(seed)
+    ids = rng.integers(0, P, size=(n_links, 3))
+    ids[:, 0] = np.arange(n_links) % P
+    lab = (rng.random(n_links) < 0.1).astype(int)
+    cnt = np.stack([1 - lab, lab], axis=1)
+    theta = rng.dirichlet(np.ones(K), size=P).tolist()
+    pr = rng.random((K, K, K, 2))
+    pr = (pr / pr.sum(axis=3, keepdims=True)).tolist()
+    deg_ok = np.bincount(ids.ravel(), minlength=P)
+    # genes without a link in this sample would raise ZeroDivisionError; restrict theta to covered genes
+    remap = -np.ones(P, dtype=int)
+    used = np.nonzero(deg_ok)[0]
+    remap[used] = np.arange(len(used))
+    ids = remap[ids]
+    theta = [theta[g] for g in used]
+    t0 = time.perf_counter()
+    orc.em_step_loops(theta, pr, ids.tolist(), cnt.tolist())
+    return time.perf_counter() - t0
+
+
+def cpu_port_rate(links_per_core: int, P: int, K: int, steps: int = 1):
+    """CPython loops on every host core, one independent sample per core (stand-in for the
+    reference's `parallel --jobs N` over samples).  Returns (link-updates/s, cores, seconds)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    total_t, total_links = 0.0, 0
+    with ctx.Pool(cores) as pool:
+        for s in range(steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(1000 + s * cores + c, links_per_core, P, K) for c in range(cores)])
+            total_t += time.perf_counter() - t0
+            total_links += links_per_core * cores
+    return total_links / total_t, cores, total_t
+
+
+def c_port_rate(n_links: int, P: int, K: int):
+    """The literal-order C oracle with OpenMP on all cores (context only)."""
+    import numpy as np
+    from oracle import mmsbm_oracle as orc
+    rng = np.random.default_rng(5)
+    ids = rng.integers(0, P, size=(n_links, 3))
+    lab = (rng.random(n_links) < 0.1).astype(np.int64)
+    cnt = np.stack([1 - lab, lab], axis=1)
+    theta = rng.dirichlet(np.ones(K), size=P)
+    pr = rng.random((K, K, K, 2))
+    pr /= pr.sum(axis=3, keepdims=True)
+    cores = os.cpu_count() or 1
+    orc.em_stats_c_mt(theta, pr, ids[:1000], cnt[:1000], cores)
+    t0 = time.perf_counter()
+    orc.em_stats_c_mt(theta, pr, ids, cnt, cores)
+    return n_links / (time.perf_counter() - t0), cores
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path.  The reference is pure
+    Python and cannot travel to the GPU box, so the oracle's literal-loop port is timed (kind "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    links_per_core = 1500
+    cpu_port_rate(100, P_GENES, K_GROUPS)                     # warm-up: imports, pool start
+    t_all, rates, cores = [], [], 1
+    budget_s, t_begin = 150.0, time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        rate, cores, secs = cpu_port_rate(links_per_core, P_GENES, K_GROUPS)
+        rates.append(rate)
+        t_all.append(secs)
+        if time.perf_counter() - t_begin > budget_s:
+            break                                             # bounded: the whole run stays within minutes
+    steps = len(rates)
+    value = sum(rates) / steps
+    sample = "%d cores x %d links per step, CPython literal-loop oracle port, K=%d, P=%d" % (
+        cores, links_per_core, K_GROUPS, P_GENES)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": 1e3 * sum(t_all) / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2 shape (6000 genes, K=10): bounded sample of %d links per step" % (links_per_core * cores)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "pypy3": "unavailable in image"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    from trigenicinteractionpredictor_b200 import _cabi, synth
+    from trigenicinteractionpredictor_b200 import dist as tdist
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+
+    rank, world, local = tdist.init_from_env()
+    if not torch.cuda.is_available():
+        raise _cabi.TipLibraryError("bench.py needs a CUDA device (no CPU path exists)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _cabi.load()
+    P, K = P_GENES, K_GROUPS
+    if args.workload == "cfg4":
+        lo, hi = tdist.shard_bounds(CFG4_LINKS, rank, world)
+        L_local, L_total, scaling = hi - lo, CFG4_LINKS, "strong"
+        workload = "cfg4: 6000 genes x 1e8 triplets, K=10, link-sharded over %d GPU(s)" % world
+    else:
+        L_local, L_total, scaling = L_PER_GPU, L_PER_GPU * world, "weak"
+        workload = ("cfg2: 6000 genes x 1M triplets, K=10, fold-1 train split = 800,000 links per GPU"
+                    + ("" if world == 1 else "; %d link shards, allreduce of statistics per iteration" % world))
+
+    group = torch.distributed.group.WORLD if world > 1 else None
+    eng = EMEngine(P, K, device=dev, group=group)
+    g1, g2, g3, lab = synth.planted_links_soa(P, L_local, seed=100 + rank, device=dev)
+    g1[:P] = torch.arange(P, dtype=torch.int32, device=dev)            # every gene has a training link
+    eng.set_train_links(g1, g2, g3, 1 - lab, lab)
+    del g1, g2, g3, lab
+    rng = np.random.default_rng(0)
+    theta0 = rng.dirichlet(np.ones(K), size=P)
+    pr0 = rng.random((K, K, K, 2))
+    pr0 /= pr0.sum(axis=3, keepdims=True)
+    eng.set_params(theta0, pr0)
+
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)    # 4x the 126 MB L2
+
+    def flush_l2():
+        flush.zero_()
+
+    # one iteration captured in a CUDA graph (E-step, allreduce, M-step)
+    eng.em_iteration()
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    before = eng.launches
+    with torch.cuda.graph(graph):
+        eng.em_iteration()
+    launches_per_step = eng.launches - before
+    eng.set_params(theta0, pr0)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        flush_l2()
+        graph.replay()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    tdist.barrier(group)
+    torch.cuda.synchronize(dev)
+    for i in range(args.steps):
+        flush_l2()
+        ev0[i].record()
+        graph.replay()
+        ev1[i].record()
+    torch.cuda.synchronize(dev)
+    tdist.barrier(group)
+    local_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    total_ms = tdist.max_over_ranks(local_ms, device=dev, group=group)
+    ms_per_step = total_ms / args.steps
+    value = L_total / (ms_per_step * 1e-3)
+
+    # back-to-back replays, rows resident in L2 (how a real training run behaves) - informational
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        graph.replay()
+    b.record()
+    torch.cuda.synchronize(dev)
+    warm_ms = tdist.max_over_ranks(a.elapsed_time(b) / args.steps, device=dev, group=group)
+
+    # dominant kernel alone (E-step): CUDA events on the launching stream, L2 flushed before each
+    k_ms = []
+    for _ in range(max(5, min(args.steps, 20))):
+        flush_l2()
+        a.record()
+        eng.em_step()
+        b.record()
+        torch.cuda.synchronize(dev)
+        k_ms.append(a.elapsed_time(b))
+    clocks = sampler.stop()
+    kernel_ms = statistics.mean(k_ms)
+    n_rows = eng.train.n_rows
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "P": P, "K": K, "links_per_gpu": L_local, "links_total": L_total,
+                   "l2": "flushed (512 MB memset) before every timed step", "cuda_graph": True},
+        "value_l2_warm": L_total / (warm_ms * 1e-3),
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+
+    if rank == 0:
+        # ---- roofline of the E-step kernel against the fp64 FMA peak measured now ----
+        peak64, peak32 = _measure_peak(lib, 0), _measure_peak(lib, 1)
+        flops = 6.0 * K ** 3 * L_local
+        achieved = flops / (kernel_ms * 1e-3) / 1e12
+        peaks = _read_peaks()
+        line["roofline"] = {
+            "bound": "fp64_fma", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s", "frac": achieved / peak64,
+            "traffic": None, "kernel": "em_fused_kernel<10>", "kernel_ms": kernel_ms,
+            "flops_per_link_update": 6 * K ** 3, "peak_source": "tip_measure_fma_peak(DFMA) in this run",
+            "fp32_fma_peak": peak32,
+            "hbm": {"algorithmic_bytes": 16 * n_rows, "achieved_gbs": 16 * n_rows / (kernel_ms * 1e-3) / 1e9,
+                    "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json" if peaks else "absent"},
+        }
+    else:
+        line["roofline"] = None
+
+    # ---- end to end through host buffers ----
+    e2e = _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist)
+    line["e2e"] = e2e
+
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            rate, cores, secs = cpu_port_rate(1500, P, K)
+            crate, ccores = c_port_rate(40000, P, K)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d cores x 1500 links, one CPython literal-loop EM step each (%.1f s); "
+                          "cost is linear in links" % (cores, secs),
+                "c_port_openmp_value": crate, "c_port_cores": ccores, "pypy3": "unavailable in image"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def _measure_peak(lib, kind):
+    import ctypes
+    out = ctypes.c_double(0.0)
+    rc = lib.tip_measure_fma_peak(kind, ctypes.byref(out))
+    if rc != 0:
+        raise RuntimeError("tip_measure_fma_peak failed: %s" % lib.tip_last_error())
+    return out.value
+
+
+def _read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh)
+    except Exception:  # noqa: BLE001
+        return {}
+
+
+def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
+    """Same metric with HOST buffers: per step copy rows + theta + p in, run one iteration, copy theta + p out."""
+    import numpy as np
+    import torch
+    P, K = eng.P, eng.K
+    rows_h = eng.train.rows.cpu().pin_memory()
+    deg_h = eng.train.deg.cpu().pin_memory()
+    th_h = torch.from_numpy(np.ascontiguousarray(theta0)).pin_memory()
+    p_h = torch.from_numpy(np.ascontiguousarray(pr0)).pin_memory()
+    h2d = rows_h.numel() * 4 + deg_h.numel() * 4 + th_h.numel() * 8 + p_h.numel() * 8
+    d2h = th_h.numel() * 8 + p_h.numel() * 8
+    steps = args.steps
+    if world == 1:
+        def step():
+            rc = lib.tip_em_iterations_host(P, K, rows_h.data_ptr(), eng.train.n_rows, eng.train.n_rows_r0,
+                                            deg_h.data_ptr(), th_h.data_ptr(), p_h.data_ptr(), 1, 0)
+            if rc != 0:
+                raise RuntimeError(lib.tip_last_error())
+        api = "tip_em_iterations_host (C ABI, pinned host buffers)"
+    else:
+        def step():
+            eng.train.rows.copy_(rows_h, non_blocking=True)
+            eng.theta.copy_(th_h.view(-1), non_blocking=True)
+            eng.p.copy_(p_h.view(-1), non_blocking=True)
+            eng.em_iteration()
+            th_h.view(-1).copy_(eng.theta, non_blocking=True)
+            p_h.view(-1).copy_(eng.p, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        api = "EMEngine.em_iteration with pinned host copies (link-sharded, NCCL allreduce)"
+    for _ in range(3):
+        step()
+    tdist.barrier(group)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    dt = tdist.max_over_ranks(dt, device=dev, group=group)
+    return {"value": L_total * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": 1e3 * dt / steps, "api": api}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=["cfg2", "cfg4"], default="cfg2")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,125 @@
+/* tip.h - C ABI of libtip.so: the B200 (sm_100a) implementation of the MMSBM EM hot path of
+ * AleixMT/TrigenicInteractionPredictor.
+ *
+ * The reference has no FFI of its own: the hot path is the Python class `Model` in
+ * src/TrigenicInteractionPredictor.py (TIP.py).  Each entry point below replaces the arithmetic
+ * of one `Model` method; the Python `Model` in trigenicinteractionpredictor_b200/ binds them
+ * with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; tip_last_error() gives the message
+ *     (thread-local).  Nothing here ever falls back to the CPU.
+ *   - pointers named d_* are DEVICE pointers owned by the caller (PyTorch tensors on the Python
+ *     side); h_* are HOST pointers.  No ownership is transferred, no device memory is allocated
+ *     by the d_* functions: scratch is passed in (`*_workspace_bytes` tells how much).
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  All d_* functions are
+ *     asynchronous on that stream and CUDA-graph capturable unless stated otherwise.
+ *   - doubles are IEEE fp64.  Layouts follow the reference: theta[P][K], p[K][K][K][2] row-major.
+ *
+ * Link rows ("packed rows"): one int4 per (link, rating) with a non-zero count:
+ *     {a, b, c, (count << 1) | rating}   a,b,c = gene ids in the reference's key slot order
+ * (decimal-string sort, TIP.py:353).  Rows are ordered rating 0 first, then rating 1, each block
+ * sorted by slot-a gene and padded with zero-count rows to a multiple of 32, so that every warp
+ * tile of 32 rows has one rating.  16 bytes per link-update is the algorithmic HBM traffic.
+ *
+ * Statistics buffer ("stats"), tip_stats_len(P,K) doubles - the quantity that is summed across
+ * link shards (one NCCL allreduce per EM iteration):
+ *     [0, P*K)                 Ntheta[g][k]   = sum over links/slots of omega * n     (TIP.py:1009-1011)
+ *     [P*K, P*K + 2*K^3)       S[r][a][b][c]  = sum_l n_lr/d_lr * th_a th_b th_c     (npr = p * S, TIP.py:1012)
+ *     [P*K + 2*K^3]            sum_l n_lr * log(d_lr) of the parameters the step STARTED from
+ */
+#ifndef TIP_H_
+#define TIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIP_ABI_VERSION 1
+#define TIP_EPS 1e-10 /* TIP.py:88 */
+#define TIP_R 2       /* TIP.py:79 */
+#define TIP_MAX_K 32
+
+/* flags for tip_em_step */
+#define TIP_EM_DEFAULT 0u
+#define TIP_EM_FORCE_GENERIC 1u /* use the any-K kernels even where a K-specialised kernel exists */
+#define TIP_EM_FP32_COMPUTE 2u  /* fp32 products / fp64 accumulation (1e-5 mode); not in ABI v1 kernels yet */
+
+int tip_abi_version(void);
+const char *tip_last_error(void);
+
+/* number of doubles in the statistics buffer */
+int64_t tip_stats_len(int P, int K);
+
+/* ---- link digestion on the device (replaces the per-iteration key parsing of TIP.py:987-989) ----
+ * in : d_g1,d_g2,d_g3 [L] gene ids in key slot order; d_n0,d_n1 [L] counts per rating (TIP.py:361-368)
+ * out: d_rows [>= tip_rows_capacity(L)] packed rows; *h_n_rows = padded row count (multiple of 32);
+ *      h_part[0..2] = {rows in the rating-0 block (padded), rows in the rating-1 block (padded),
+ *                      real (unpadded) rows};  d_deg [P] int32 = distinct links touching each gene
+ *      (the `counter` of TIP.py:986-994).  d_deg may be NULL.
+ * Synchronises the stream (it returns counts to the host); digestion time, not iteration time. */
+int64_t tip_rows_capacity(int64_t L);
+int tip_pack_rows_workspace_bytes(int64_t L, size_t *bytes);
+int tip_pack_rows(const int32_t *d_g1, const int32_t *d_g2, const int32_t *d_g3, const int32_t *d_n0,
+                  const int32_t *d_n1, int64_t L, int P, void *d_ws, size_t ws_bytes, void *d_rows,
+                  int64_t *h_n_rows, int64_t *h_part, int32_t *d_deg, void *stream);
+
+/* ---- Model.make_iteration, E-step half (TIP.py:987-1012) ----
+ * Zeroes d_stats, then accumulates the statistics of `n_rows` packed rows under (d_theta, d_p).
+ * n_rows_r0 = rows in the rating-0 block (h_part[0] of tip_pack_rows); both are multiples of 32.
+ * d_ws: tip_em_workspace_bytes() bytes of scratch (0 for the K-specialised kernels; may be NULL then). */
+int tip_em_workspace_bytes(int P, int K, int64_t n_rows, unsigned flags, size_t *bytes);
+int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int64_t n_rows_r0, const double *d_theta,
+                const double *d_p, double *d_stats, void *d_ws, size_t ws_bytes, unsigned flags, void *stream);
+
+/* ---- Model.make_iteration, M-step half (TIP.py:1016-1043) ----
+ * theta[g][k] = Ntheta[g][k] / deg[g];  npr = p*S;  p = npr / (eps + npr0 + npr1).  In place on d_p.
+ * Genes with deg == 0 produce inf/nan like a float division would; the Python Model raises
+ * ZeroDivisionError before launching, as TIP.py:1018 does. */
+int tip_normalise(int P, int K, const double *d_stats, const int32_t *d_deg, double *d_theta, double *d_p,
+                  void *stream);
+
+/* ---- Model.compute_likelihood (TIP.py:952-974) ----
+ * *d_out = sum_rows count * log(eps + sum_abc th th th p_r).  Deterministic summation order.
+ * d_ws: tip_loglik_workspace_bytes() bytes of scratch. */
+size_t tip_loglik_workspace_bytes(void);
+int tip_loglik(int P, int K, const void *d_rows, int64_t n_rows, const double *d_theta, const double *d_p,
+               double *d_out, void *d_ws, void *stream);
+
+/* ---- Model.do_prediction over a whole test set (TIP.py:530-547, 564-565) ----
+ * d_scores[t] = sum_abc th[g1[t]][a] th[g2[t]][b] th[g3[t]][c] p[a][b][c][1]   (no eps). */
+int tip_score(int P, int K, const int32_t *d_g1, const int32_t *d_g2, const int32_t *d_g3, int64_t T,
+              const double *d_theta, const double *d_p, double *d_scores, void *stream);
+
+/* ---- Model.calculate_metrics (TIP.py:583-637), integer part ----
+ * d_out[8] int64 = {auc_wins (#(pos,neg) with score_pos > score_neg, strict), n_pos, n_neg,
+ *                   tp, fp, fn, tn, bit pattern of cut_value}
+ * positives_number = int(positives_fraction * T) computed by the caller (TIP.py:592); cut_value is
+ * the positives_number-th largest score, or 0.0 when positives_number >= T (TIP.py:595-599).
+ * The ratios are formed by the caller in Python so ZeroDivisionError behaves as in the reference. */
+int tip_metrics_workspace_bytes(int64_t T, size_t *bytes);
+int tip_metrics(const double *d_scores, const int32_t *d_labels, int64_t T, int64_t positives_number,
+                void *d_ws, size_t ws_bytes, int64_t *d_out, void *stream);
+
+/* ---- host-buffer entry: n_iter full make_iteration()s with HOST inputs and outputs ----
+ * Copies rows/deg/theta/p to the device, runs n_iter x (E-step, M-step), copies theta/p back and
+ * synchronises.  Allocates and frees its own device memory (the only function that does).
+ * This is the call bench.py times for the end-to-end number. */
+int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t n_rows, int64_t n_rows_r0,
+                           const int32_t *h_deg, double *h_theta, double *h_p, int n_iter, unsigned flags);
+
+/* ---- roofline denominators: measured FMA peak of this GPU ----
+ * kind 0: fp64 DFMA, 1: fp32 FFMA, 2: fp64 mma.sync (DMMA m8n8k4), 3: DFMA and DMMA interleaved.
+ * Returns TFLOP/s (2 flops per FMA) in *tflops; runs on the current device, synchronous. */
+int tip_measure_fma_peak(int kind, double *tflops);
+/* scattered fp64 red.global.add throughput over `n_addr` doubles: G atomics/s in *gops.
+ * mode 0: one random address per lane; mode 1: row-contiguous runs of 10 doubles. */
+int tip_measure_red_f64(int64_t n_addr, int mode, double *gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIP_H_ */

@@ -1,0 +1,288 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`).  Everything goes through the C ABI
+(libtip.so) via the drop-in Model / EMEngine and is compared with
+  * the golden vectors produced by the unmodified reference (tests/golden), and
+  * the CPU oracle on the same seeded inputs,
+then, at BASELINE.json's full sizes, through size-independent properties.
+Tolerances: ids / folds / packing bit-exact; theta, p, log-likelihood 1e-9 relative (fp64 mode);
+AUC 1e-6 (north_star)."""
+import ctypes
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+BASE = os.path.join(GOLDEN, "base")
+DUPS = os.path.join(GOLDEN, "dups")
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _model(case, train, test, **kw):
+    from trigenicinteractionpredictor_b200 import Model
+    m = Model(**kw)
+    m.get_traintest(os.path.join(case, train), os.path.join(case, test))
+    return m
+
+
+def _relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["specialised", "anyK"])
+@pytest.mark.parametrize("K", [1, 2, 3, 10])
+def test_em_trace_matches_reference(torch_cuda, K, flags):
+    tr = np.load(os.path.join(BASE, "trace_K%d.npz" % K))
+    m = _model(BASE, "train1.dat", "test1.dat", flags=flags)
+    random.seed(1000)
+    m.initialize_parameters(K)
+    assert np.array_equal(np.array(m.theta), tr["theta0"])
+    assert m.compute_likelihood() == pytest.approx(tr["loglik"][0], rel=RTOL)
+    for it in range(5):
+        m.make_iteration()
+        assert _relerr(m.theta, tr["theta%d" % (it + 1)]) < RTOL, "theta iteration %d" % (it + 1)
+        assert _relerr(m.pr, tr["pr%d" % (it + 1)]) < RTOL, "p iteration %d" % (it + 1)
+        assert m.compute_likelihood() == pytest.approx(tr["loglik"][it + 1], rel=RTOL)
+        assert m.likelihood == pytest.approx(tr["loglik"][it + 1], rel=RTOL)
+    assert m.compute_likelihood("test") == pytest.approx(tr["heldout"][0], rel=RTOL)
+    # scoring, table order and metrics
+    m.calculate_test_set_results()
+    sc = m._scores.cpu().numpy()
+    assert _relerr(sc, tr["scores_test_order"]) < RTOL
+    res = m.results
+    assert len(res) == len(tr["result_keys"])
+    assert _relerr([r[0] for r in res], tr["result_scores"]) < RTOL
+    same = sum(1 for r, k in zip(res, tr["result_keys"].tolist()) if r[1] == k)
+    assert same >= len(res) - 4, "sorted test table differs beyond near-tie swaps"
+    met = m.calculate_metrics()
+    assert met[3] == pytest.approx(tr["metrics"][3], abs=1e-6)          # AUC
+    np.testing.assert_allclose(met[:3], tr["metrics"][:3], atol=1e-2)   # rank-cut counts may move by one on a tie
+    # single-triplet prediction by id strings and by gene names (TIP.py:541-545)
+    key = next(iter(m.test_links)).split("_")
+    names = [m.id_gene[int(t)] for t in key]
+    assert m.do_prediction(*key) == pytest.approx(tr["predict_by_name"][1], rel=RTOL)
+    assert m.do_prediction(*names) == pytest.approx(tr["predict_by_name"][0], rel=RTOL)
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["specialised", "anyK"])
+def test_duplicates_conflicts_and_string_sorted_slots(torch_cuda, flags):
+    tr = np.load(os.path.join(DUPS, "trace_K3.npz"))
+    m = _model(DUPS, "train.dat", "test.dat", flags=flags)
+    random.seed(1001)
+    m.initialize_parameters(3)
+    for it in range(3):
+        m.make_iteration()
+        assert _relerr(m.theta, tr["theta%d" % (it + 1)]) < RTOL
+        assert _relerr(m.pr, tr["pr%d" % (it + 1)]) < RTOL
+        assert m.compute_likelihood() == pytest.approx(tr["loglik"][it + 1], rel=RTOL)
+    assert m.compute_likelihood("test") == pytest.approx(tr["heldout"][0], rel=RTOL)
+    m.calculate_test_set_results()
+    assert _relerr(m._scores.cpu().numpy(), tr["scores_test_order"]) < RTOL
+    assert m.calculate_metrics()[3] == pytest.approx(tr["metrics"][3], abs=1e-6)
+
+
+def test_gene_seen_only_in_test_raises_like_reference(torch_cuda):
+    m = _model(os.path.join(GOLDEN, "testonly"), "train.dat", "test.dat")
+    random.seed(5)
+    m.initialize_parameters(2)
+    with pytest.raises(ZeroDivisionError):
+        m.make_iteration()
+
+
+def test_pack_rows_bit_exact(torch_cuda):
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    rng = np.random.default_rng(3)
+    P, L = 500, 7001
+    g = rng.integers(0, P, size=(L, 3)).astype(np.int32)
+    n0 = rng.integers(0, 3, size=L).astype(np.int32)
+    n1 = rng.integers(0, 3, size=L).astype(np.int32)
+    eng = EMEngine(P, 2)
+    pk = eng.pack(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+    rows = pk.rows.cpu().numpy()
+    exp = []
+    for r, n in ((0, n0), (1, n1)):
+        sel = np.nonzero(n > 0)[0]
+        order = np.lexsort((g[sel, 2], g[sel, 1], g[sel, 0]))
+        blk = np.stack([g[sel, 0], g[sel, 1], g[sel, 2], (n[sel] << 1) | r], axis=1)[order]
+        pad = (-len(blk)) % 32
+        blk = np.concatenate([blk, np.tile(np.array([[0, 0, 0, r]], dtype=np.int32), (pad, 1))])
+        exp.append(blk)
+    assert pk.n_rows_r0 == len(exp[0]) and pk.n_rows == len(exp[0]) + len(exp[1])
+    assert pk.n_real == int((n0 > 0).sum() + (n1 > 0).sum())
+    # rows with identical (a,b,c) may be permuted among themselves; compare as sorted tuples per block
+    for blk, lo in ((exp[0], 0), (exp[1], pk.n_rows_r0)):
+        got = rows[lo: lo + len(blk)]
+        assert np.array_equal(got[:, :3], blk[:, :3])
+        assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, blk.tolist()))
+    live = (n0 > 0) | (n1 > 0)
+    deg = np.bincount(g[live].ravel(), minlength=P)
+    assert np.array_equal(pk.deg.cpu().numpy(), deg)
+
+
+def _random_problem(P, L, K, seed):
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, P, size=(L, 3)).astype(np.int32)
+    g[:P, 0] = np.arange(P)                       # every gene has a training link
+    lab = (rng.random(L) < 0.15).astype(np.int32)
+    theta = rng.dirichlet(np.ones(K), size=P)
+    pr = rng.random((K, K, K, 2))
+    pr /= pr.sum(axis=3, keepdims=True)
+    return g, 1 - lab, lab, theta, pr
+
+
+@pytest.mark.parametrize("K", [4, 5, 6, 7, 8, 9, 10, 12, 16])
+def test_em_step_vs_oracle_all_k(torch_cuda, K):
+    from oracle import mmsbm_oracle as orc
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    P, L = 300, 6000 if K <= 10 else 1500
+    g, n0, n1, theta, pr = _random_problem(P, L, K, 10 + K)
+    cnt = np.stack([n0, n1], axis=1).astype(np.int64)
+    ent, enp, deg = orc.em_step_np(theta, pr, g.astype(np.int64), cnt, return_stats=True)
+    ll = orc.loglik_np(theta, pr, g.astype(np.int64), cnt)
+    th1, pr1 = orc.normalise_np(ent, enp, deg)
+    for flags in ([0, 1] if K <= 10 else [0]):
+        eng = EMEngine(P, K, flags=flags)
+        eng.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+        eng.set_params(theta, pr)
+        eng.em_step()
+        st = eng.stats.cpu().numpy()
+        nth = st[: P * K].reshape(P, K)
+        S = st[P * K: P * K + 2 * K ** 3].reshape(2, K, K, K)
+        npr = pr * np.moveaxis(S, 0, -1)
+        assert _relerr(nth, ent) < 1e-11, "Ntheta K=%d flags=%d" % (K, flags)
+        assert _relerr(npr, np.maximum(enp, 1e-300)) < 1e-11, "Np K=%d flags=%d" % (K, flags)
+        assert st[-1] == pytest.approx(ll, rel=1e-12)
+        assert eng.loglik("train") == pytest.approx(ll, rel=1e-12)
+        eng.normalise()
+        th, p = eng.get_params()
+        assert _relerr(th, th1) < 1e-11 and _relerr(p, pr1) < 1e-11
+        assert np.array_equal(eng.degrees(), deg.astype(np.int32))
+
+
+def test_graph_replay_and_host_entry_equal_stepwise(torch_cuda):
+    from trigenicinteractionpredictor_b200 import _cabi
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    P, L, K = 400, 9000, 10
+    g, n0, n1, theta, pr = _random_problem(P, L, K, 77)
+    a = EMEngine(P, K)
+    a.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+    a.set_params(theta, pr)
+    for _ in range(6):
+        a.em_iteration()
+    th_a, p_a = a.get_params()
+    b = EMEngine(P, K)
+    b.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+    b.set_params(theta, pr)
+    b.em_iterations(6, use_graph=True)
+    th_b, p_b = b.get_params()
+    # atomics make the summation order run-dependent: agreement is to rounding, not bitwise
+    assert _relerr(th_b, th_a) < 1e-11 and _relerr(p_b, p_a) < 1e-11
+    # host-buffer entry point
+    lib = _cabi.load()
+    rows = np.ascontiguousarray(a.train.rows.cpu().numpy())
+    deg = np.ascontiguousarray(a.degrees().astype(np.int32))
+    th_h, p_h = np.ascontiguousarray(theta.copy()), np.ascontiguousarray(pr.copy())
+    rc = lib.tip_em_iterations_host(P, K, rows.ctypes.data, a.train.n_rows, a.train.n_rows_r0, deg.ctypes.data,
+                                    th_h.ctypes.data, p_h.ctypes.data, 6, 0)
+    assert rc == 0, lib.tip_last_error()
+    assert _relerr(th_h, th_a) < 1e-11 and _relerr(p_h, p_a) < 1e-11
+
+
+def test_metrics_kernel_vs_reference_loops(torch_cuda):
+    torch = torch_cuda
+    from oracle import mmsbm_oracle as orc
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    rng = np.random.default_rng(5)
+    T = 3000
+    scores = np.round(rng.random(T), 2)            # many exact ties
+    n0 = (rng.random(T) < 0.8).astype(np.int32)
+    g = rng.integers(0, 50, size=(T, 3)).astype(np.int32)
+    eng = EMEngine(50, 2)
+    eng.set_test_links(g[:, 0], g[:, 1], g[:, 2], n0, 1 - n0)
+    test_links = {"%d" % i: [int(n0[i]), int(1 - n0[i])] for i in range(T)}
+    res = orc.test_results(scores, test_links)
+    train_links = {"a": [0, 1], "b": [1, 0], "c": [1, 0], "d": [1, 0], "e": [0, 1]}
+    exp = orc.metrics_quadratic(res, train_links, T)
+    npos_rank = int(2 / 5 * T)
+    c = eng.metric_counts(torch.from_numpy(scores).to(eng.device), npos_rank)
+    got = [c["tp"] / (c["tp"] + c["fp"]), c["tp"] / (c["tp"] + c["fn"]), c["fp"] / (c["fp"] + c["tn"]),
+           c["wins"] / (c["n_pos"] * c["n_neg"])]
+    assert got == exp                               # integers -> identical floats
+    assert c["cut_value"] == res[npos_rank][0]
+    big = eng.metric_counts(torch.from_numpy(scores).to(eng.device), T + 5)   # index past the end: cut stays 0
+    assert big["cut_value"] == 0.0 and big["fn"] == 0 and big["tn"] == 0
+
+
+def test_training_loop_and_report_match_reference(torch_cuda, tmp_path):
+    from trigenicinteractionpredictor_b200 import train_sample
+    man = json.load(open(os.path.join(GOLDEN, "manifest.json")))["base"]["loop"]
+    m = _model(BASE, "train1.dat", "test1.dat")
+    random.seed(1000)
+    out = str(tmp_path / "Sample_0_K2.csv")
+    conv, done, checks = train_sample(m, man["K"], man["iterations"], man["fcheck"], man["bcheck"], outfile=out,
+                                      verbose=False)
+    assert conv and done - 1 == man["converged_at_iteration"]
+    np.testing.assert_allclose(checks, man["checks"], rtol=RTOL)
+    got = open(out, encoding="utf-8").read().split("\n")
+    exp = open(os.path.join(BASE, "Sample_0_K2.csv"), encoding="utf-8").read().split("\n")
+    assert len(got) == len(exp)
+    swaps = 0
+    for lg, le in zip(got, exp):
+        fg, fe = lg.split("\t"), le.split("\t")
+        assert len(fg) == len(fe)
+        for xg, xe in zip(fg, fe):
+            if xg == xe:
+                continue
+            try:
+                assert float(xg) == pytest.approx(float(xe), rel=1e-8, abs=1e-12), (lg, le)
+            except ValueError:
+                swaps += 1                          # a key column differing: near-tie swap in the table
+    assert swaps <= 4
+
+
+def test_full_size_properties_cfg2(torch_cuda):
+    """BASELINE config 2 shape (6,000 genes, 800k training links, K=10): invariants of one EM step."""
+    torch = torch_cuda
+    from trigenicinteractionpredictor_b200 import synth
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    P, L, K = 6000, 800_000, 10
+    g1, g2, g3, lab = synth.planted_links_soa(P, L, seed=11, device="cuda")
+    g1[:P] = torch.arange(P, dtype=torch.int32, device="cuda")
+    rng = np.random.default_rng(0)
+    theta = rng.dirichlet(np.ones(K), size=P)
+    pr = rng.random((K, K, K, 2))
+    pr /= pr.sum(axis=3, keepdims=True)
+    outs = []
+    for flags in (0, 1):
+        eng = EMEngine(P, K, flags=flags)
+        eng.set_train_links(g1, g2, g3, 1 - lab, lab)
+        assert eng.train.n_real == L
+        eng.set_params(theta, pr)
+        ll0 = eng.loglik("train")
+        eng.em_step()
+        st = eng.stats.cpu().numpy()
+        assert st[-1] == pytest.approx(ll0, rel=1e-12)          # by-product == dedicated reduction
+        S = st[P * K: P * K + 2 * K ** 3].reshape(2, K, K, K)
+        npr = pr * np.moveaxis(S, 0, -1)
+        # every link distributes (d-eps)/d ~ 1 unit of responsibility: over cells and over each slot
+        assert npr.sum() == pytest.approx(L, rel=1e-6)
+        assert st[: P * K].sum() == pytest.approx(3 * L, rel=1e-6)
+        eng.normalise()
+        th, p = eng.get_params()
+        np.testing.assert_allclose(th.sum(axis=1), 1.0, atol=1e-6)      # trap 2: count-1 data keeps rows on the simplex
+        np.testing.assert_allclose(p.sum(axis=3), 1.0, atol=1e-6)
+        assert eng.loglik("train") > ll0                                 # EM ascent
+        outs.append((th, p))
+    assert _relerr(outs[0][0], outs[1][0]) < 1e-10 and _relerr(outs[0][1], outs[1][1]) < 1e-10

@@ -1,0 +1,128 @@
+"""Host-side logic of the drop-in Model (no GPU): digestion, fold, init, CLI parsing - bit-exact
+against the vectors the reference produced (tests/golden, see oracle/gen_golden.py)."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from tests.conftest import GOLDEN
+from trigenicinteractionpredictor_b200 import Model, main
+from trigenicinteractionpredictor_b200 import dist as tdist
+
+BASE = os.path.join(GOLDEN, "base")
+DUPS = os.path.join(GOLDEN, "dups")
+
+
+def _load(case, train, test):
+    m = Model()
+    m.get_traintest(os.path.join(case, train), os.path.join(case, test))
+    return m
+
+
+def _check(m, rec):
+    assert m.P == rec["P"]
+    assert [m.id_gene[i] for i in range(m.P)] == rec["genes_in_id_order"]
+    assert [m.uniqueg[i] for i in range(m.P)] == rec["uniqueg"]
+    assert list(m.links.keys()) == rec["link_keys"]
+    assert [list(v) for v in m.links.values()] == rec["link_counts"]
+    assert list(m.nlinks.keys()) == rec["nlink_keys"]
+    assert list(m.test_links.keys()) == rec["test_keys"]
+    assert [list(v) for v in m.test_links.values()] == rec["test_counts"]
+    assert m.gene_id == {v: k for k, v in m.id_gene.items()}
+
+
+def test_get_traintest_bit_exact(capsys):
+    m = _load(BASE, "train1.dat", "test1.dat")
+    _check(m, json.load(open(os.path.join(BASE, "digest.json"))))
+    out = capsys.readouterr().out
+    assert "READ DATA train 1600 1600" in out and "READ DATA test 400" in out
+
+
+def test_get_traintest_dups():
+    _check(_load(DUPS, "train.dat", "test.dat"), json.load(open(os.path.join(DUPS, "digest.json"))))
+
+
+def test_get_input_and_fold_bit_exact(tmp_path, monkeypatch):
+    man = json.load(open(os.path.join(GOLDEN, "manifest.json")))["base"]
+    m = Model()
+    m.get_input(os.path.join(BASE, "input_s2.tsv"))
+    assert [m.id_gene[i] for i in range(m.P)] == man["get_input"]["genes_in_id_order"]
+    assert list(m.links)[:50] == man["get_input"]["link_keys_head"]
+    assert len(m.links) == man["get_input"]["n_links"]
+    assert sum(1 for v in m.links.values() if v[1]) == man["get_input"]["n_pos"]
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(2)
+    m.fold()
+    for i in range(5):
+        for kind in ("test", "train"):
+            name = "%s%d.dat" % (kind, i)
+            assert open(name, "rb").read() == open(os.path.join(BASE, name), "rb").read(), name
+
+
+def test_fold_remainder_goes_to_last_fold(tmp_path, monkeypatch):
+    m = Model()
+    for i in range(13):
+        m.gene_id["g%d" % i] = i
+        m.id_gene[i] = "g%d" % i
+    for i in range(11):
+        m.links["%d_%d_%d" % (i, i + 1, i + 2)] = [1, 0] if i % 3 else [0, 1]
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(0)
+    m.fold(0.2)
+    sizes = [len(open("test%d.dat" % i).readlines()) for i in range(5)]
+    assert sizes == [2, 2, 2, 2, 3]
+    assert [len(open("train%d.dat" % i).readlines()) for i in range(5)] == [9, 9, 9, 9, 8]
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 10])
+def test_initialize_parameters_bit_exact(K):
+    m = _load(BASE, "train1.dat", "test1.dat")
+    tr = np.load(os.path.join(BASE, "trace_K%d.npz" % K))
+    random.seed(1000)
+    m.initialize_parameters(K)
+    assert np.array_equal(np.array(m.theta), tr["theta0"])
+    assert np.array_equal(np.array(m.pr), tr["pr0"])
+    assert random.random() == tr["after_init_random"][0]
+    assert m.K == K and m.vlikelihood == []
+    assert np.array(m.ntheta).shape == (m.P, K) and not np.array(m.npr).any()
+
+
+def test_initialize_parameters_bad_k_defaults_to_10():
+    m = Model()
+    m.P = 3
+    m.initialize_parameters("not-a-number")
+    assert m.K == 10 and len(m.theta[0]) == 10
+
+
+def test_numeric_methods_fail_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from trigenicinteractionpredictor_b200._cabi import TipLibraryError
+    m = _load(BASE, "train1.dat", "test1.dat")
+    m.initialize_parameters(2)
+    with pytest.raises(TipLibraryError):
+        m.make_iteration()
+    with pytest.raises(TipLibraryError):
+        m.compute_likelihood()
+
+
+def test_cli_rejects_bad_arguments(tmp_path, capsys):
+    assert main(["--bogus"]) == 2
+    assert main(["-k", "0", "-t", os.path.join(BASE, "train1.dat"), "-e", os.path.join(BASE, "test1.dat")]) == 2
+    assert main(["-t", "/nonexistent", "-e", os.path.join(BASE, "test1.dat")]) == 2
+    assert main(["-o", str(tmp_path / "missing"), "-t", os.path.join(BASE, "train1.dat")]) == 2
+    assert main(["-h"]) == 0
+
+
+def test_shard_bounds_and_sample_assignment():
+    for n, w in [(10, 3), (100_000_000, 8), (5, 8), (0, 2)]:
+        spans = [tdist.shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+    per = [len(tdist.samples_for_rank(0, 50, r, 8)) for r in range(8)]
+    assert per == [7, 7, 6, 6, 6, 6, 6, 6]
+    assert sorted(s for r in range(8) for s in tdist.samples_for_rank(10, 50, r, 8)) == list(range(10, 60))

@@ -1,0 +1,294 @@
+// extern "C" surface of libtip.so (see include/tip.h), the host-buffer entry and the peak probes.
+#include <stdarg.h>
+#include <string.h>
+
+#include <chrono>
+
+#include "tip_common.cuh"
+
+namespace tip {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static bool valid_K(int K) { return K >= 1 && K <= TIP_MAX_K; }
+
+}  // namespace tip
+
+using namespace tip;
+
+extern "C" int tip_abi_version(void) { return TIP_ABI_VERSION; }
+extern "C" const char *tip_last_error(void) { return g_err; }
+
+extern "C" int64_t tip_stats_len(int P, int K) { return (int64_t)P * K + 2ll * K * K * K + 1; }
+
+extern "C" int tip_em_workspace_bytes(int P, int K, int64_t n_rows, unsigned flags, size_t *bytes)
+{
+    TIP_REQUIRE(bytes != nullptr && P > 0 && valid_K(K) && n_rows >= 0, "tip_em_workspace_bytes: bad arguments");
+    const bool tuned = !(flags & TIP_EM_FORCE_GENERIC) && K <= 10;
+    *bytes = tuned ? 0 : (size_t)(n_rows < 1 ? 1 : n_rows) * sizeof(double);
+    return 0;
+}
+
+extern "C" int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int64_t n_rows_r0, const double *d_theta,
+                           const double *d_p, double *d_stats, void *d_ws, size_t ws_bytes, unsigned flags, void *stream)
+{
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TIP_REQUIRE(P > 0 && valid_K(K), "tip_em_step: need P > 0 and 1 <= K <= %d (got P=%d K=%d)", TIP_MAX_K, P, K);
+    TIP_REQUIRE(n_rows >= 0 && n_rows % 32 == 0 && n_rows_r0 >= 0 && n_rows_r0 <= n_rows && n_rows_r0 % 32 == 0,
+                "tip_em_step: n_rows (%lld) and n_rows_r0 (%lld) must be multiples of 32 from tip_pack_rows",
+                (long long)n_rows, (long long)n_rows_r0);
+    TIP_REQUIRE(d_theta && d_p && d_stats && (d_rows || n_rows == 0), "tip_em_step: null pointer");
+    TIP_REQUIRE(!(flags & TIP_EM_FP32_COMPUTE), "tip_em_step: TIP_EM_FP32_COMPUTE is not implemented in ABI v%d", TIP_ABI_VERSION);
+    TIP_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * (size_t)tip_stats_len(P, K), st));
+    if (n_rows == 0) return 0;
+    const int4 *rows = reinterpret_cast<const int4 *>(d_rows);
+    if (!(flags & TIP_EM_FORCE_GENERIC)) {
+        bool handled = false;
+        int rc = launch_em_tuned(P, K, rows, n_rows, d_theta, d_p, d_stats, st, &handled);
+        if (rc != 0 || handled) return rc;
+    }
+    TIP_REQUIRE(d_ws != nullptr && ws_bytes >= (size_t)n_rows * sizeof(double),
+                "tip_em_step: the any-K path needs %zu bytes of workspace (got %zu)", (size_t)n_rows * sizeof(double), ws_bytes);
+    return launch_em_generic(P, K, rows, n_rows, n_rows_r0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws), st);
+}
+
+extern "C" int tip_normalise(int P, int K, const double *d_stats, const int32_t *d_deg, double *d_theta, double *d_p,
+                             void *stream)
+{
+    TIP_REQUIRE(P > 0 && valid_K(K) && d_stats && d_deg && d_theta && d_p, "tip_normalise: bad arguments");
+    return launch_normalise(P, K, d_stats, d_deg, d_theta, d_p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t tip_loglik_workspace_bytes(void) { return loglik_ws_bytes(); }
+
+extern "C" int tip_loglik(int P, int K, const void *d_rows, int64_t n_rows, const double *d_theta, const double *d_p,
+                          double *d_out, void *d_ws, void *stream)
+{
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TIP_REQUIRE(P > 0 && valid_K(K) && d_theta && d_p && d_out && d_ws && n_rows >= 0, "tip_loglik: bad arguments");
+    if (n_rows == 0) {
+        TIP_CHECK_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), st));
+        return 0;
+    }
+    return launch_loglik(K, reinterpret_cast<const int4 *>(d_rows), n_rows, d_theta, d_p, d_out, d_ws, st);
+}
+
+extern "C" int tip_score(int P, int K, const int32_t *d_g1, const int32_t *d_g2, const int32_t *d_g3, int64_t T,
+                         const double *d_theta, const double *d_p, double *d_scores, void *stream)
+{
+    TIP_REQUIRE(P > 0 && valid_K(K) && T >= 0 && d_theta && d_p && (T == 0 || (d_g1 && d_g2 && d_g3 && d_scores)),
+                "tip_score: bad arguments");
+    return launch_score(K, d_g1, d_g2, d_g3, T, d_theta, d_p, d_scores, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer entry (grow-only device scratch, released with the process)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct HostPool {
+    void *rows = nullptr, *theta = nullptr, *p = nullptr, *stats = nullptr, *deg = nullptr, *ws = nullptr;
+    size_t rows_b = 0, theta_b = 0, p_b = 0, stats_b = 0, deg_b = 0, ws_b = 0;
+    cudaStream_t st = nullptr;
+};
+HostPool g_pool;
+
+int ensure(void **ptr, size_t *have, size_t need)
+{
+    if (*have >= need && *ptr) return 0;
+    if (*ptr) TIP_CHECK_CUDA(cudaFree(*ptr));
+    *ptr = nullptr;
+    *have = 0;
+    TIP_CHECK_CUDA(cudaMalloc(ptr, need < 256 ? 256 : need));
+    *have = need;
+    return 0;
+}
+}  // namespace
+
+extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t n_rows, int64_t n_rows_r0,
+                                      const int32_t *h_deg, double *h_theta, double *h_p, int n_iter, unsigned flags)
+{
+    TIP_REQUIRE(P > 0 && valid_K(K) && h_rows && h_deg && h_theta && h_p && n_iter >= 0 && n_rows >= 0,
+                "tip_em_iterations_host: bad arguments");
+    HostPool &g = g_pool;
+    if (!g.st) TIP_CHECK_CUDA(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
+    const size_t nth = (size_t)P * K * 8, np = (size_t)2 * K * K * K * 8, nst = (size_t)tip_stats_len(P, K) * 8;
+    size_t wsb = 0;
+    if (tip_em_workspace_bytes(P, K, n_rows, flags, &wsb) != 0) return -1;
+    int rc;
+    if ((rc = ensure(&g.rows, &g.rows_b, (size_t)n_rows * 16)) || (rc = ensure(&g.theta, &g.theta_b, nth)) ||
+        (rc = ensure(&g.p, &g.p_b, np)) || (rc = ensure(&g.stats, &g.stats_b, nst)) ||
+        (rc = ensure(&g.deg, &g.deg_b, (size_t)P * 4)) || (rc = ensure(&g.ws, &g.ws_b, wsb)))
+        return rc;
+    TIP_CHECK_CUDA(cudaMemcpyAsync(g.rows, h_rows, (size_t)n_rows * 16, cudaMemcpyHostToDevice, g.st));
+    TIP_CHECK_CUDA(cudaMemcpyAsync(g.deg, h_deg, (size_t)P * 4, cudaMemcpyHostToDevice, g.st));
+    TIP_CHECK_CUDA(cudaMemcpyAsync(g.theta, h_theta, nth, cudaMemcpyHostToDevice, g.st));
+    TIP_CHECK_CUDA(cudaMemcpyAsync(g.p, h_p, np, cudaMemcpyHostToDevice, g.st));
+    for (int it = 0; it < n_iter; ++it) {
+        rc = tip_em_step(P, K, g.rows, n_rows, n_rows_r0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
+                         g.ws, g.ws_b, flags, g.st);
+        if (rc) return rc;
+        rc = tip_normalise(P, K, (const double *)g.stats, (const int32_t *)g.deg, (double *)g.theta, (double *)g.p, g.st);
+        if (rc) return rc;
+    }
+    TIP_CHECK_CUDA(cudaMemcpyAsync(h_theta, g.theta, nth, cudaMemcpyDeviceToHost, g.st));
+    TIP_CHECK_CUDA(cudaMemcpyAsync(h_p, g.p, np, cudaMemcpyDeviceToHost, g.st));
+    TIP_CHECK_CUDA(cudaStreamSynchronize(g.st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// peak probes (roofline denominators are measured, not assumed)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kProbeChains = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256) fma_probe_kernel(T *out, int iters, T a, T b)
+{
+    T acc[kProbeChains];
+#pragma unroll
+    for (int i = 0; i < kProbeChains; ++i) acc[i] = (T)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kProbeChains; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    T s = 0;
+#pragma unroll
+    for (int i = 0; i < kProbeChains; ++i) s += acc[i];
+    if (s == (T)123456.789) out[0] = s;
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// mode 0: DMMA only; mode 1: DMMA + DFMA interleaved (same number of each instruction)
+template <int MODE>
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double *out, int iters, double a, double b)
+{
+    double c[8];
+    double f[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = threadIdx.x + i;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = threadIdx.x - i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            dmma_m8n8k4(c[2 * i], c[2 * i + 1], a, b);
+            if (MODE == 1) f[i] = fma(f[i], a, b);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += f[i];
+    if (s == 123456.789) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) red_probe_kernel(double *buf, int64_t n_addr, int mode, int iters)
+{
+    unsigned long long x = (blockIdx.x * 256ull + threadIdx.x) * 0x9E3779B97F4A7C15ull + 12345;
+    const int lane = threadIdx.x & 31;
+    for (int it = 0; it < iters; ++it) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        int64_t addr;
+        if (mode == 0) {
+            addr = (int64_t)(x % (unsigned long long)n_addr);
+        } else {
+            // groups of 10 lanes share one random row of 10 doubles (lanes 30,31 idle), like theta rows at K=10
+            unsigned long long xr = __shfl_sync(0xffffffffu, x, (lane / 10) * 10);
+            const int64_t rows = n_addr / 10;
+            addr = (int64_t)(xr % (unsigned long long)rows) * 10 + lane % 10;
+            if (lane >= 30) continue;
+        }
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(buf + addr), "d"(1.0) : "memory");
+    }
+}
+
+template <typename F>
+int time_kernel(F launch, double *ms_out)
+{
+    cudaEvent_t e0, e1;
+    TIP_CHECK_CUDA(cudaEventCreate(&e0));
+    TIP_CHECK_CUDA(cudaEventCreate(&e1));
+    launch();  // warm-up
+    TIP_CHECK_CUDA(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        TIP_CHECK_CUDA(cudaEventRecord(e0));
+        launch();
+        TIP_CHECK_CUDA(cudaEventRecord(e1));
+        TIP_CHECK_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        TIP_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    TIP_CHECK_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_out = best;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int tip_measure_fma_peak(int kind, double *tflops)
+{
+    TIP_REQUIRE(tflops != nullptr && kind >= 0 && kind <= 3, "tip_measure_fma_peak: kind must be 0..3");
+    double *d_out = nullptr;
+    TIP_CHECK_CUDA(cudaMalloc(&d_out, 256));
+    const int blocks = sm_count() * 8, threads = 256;
+    double ms = 0, flops = 0;
+    int rc = 0;
+    if (kind == 0) {
+        const int iters = 1 << 15;
+        rc = time_kernel([&] { fma_probe_kernel<double><<<blocks, threads>>>(d_out, iters, 1.0000001, 1e-9); }, &ms);
+        flops = 2.0 * kProbeChains * (double)iters * blocks * threads;
+    } else if (kind == 1) {
+        const int iters = 1 << 16;
+        rc = time_kernel([&] { fma_probe_kernel<float><<<blocks, threads>>>(reinterpret_cast<float *>(d_out), iters, 1.0000001f, 1e-9f); }, &ms);
+        flops = 2.0 * kProbeChains * (double)iters * blocks * threads;
+    } else if (kind == 2) {
+        const int iters = 1 << 13;
+        rc = time_kernel([&] { dmma_probe_kernel<0><<<blocks, threads>>>(d_out, iters, 1.0000001, 1e-9); }, &ms);
+        flops = 2.0 * 256.0 * 4 * (double)iters * blocks * (threads / 32);  // m8n8k4 = 256 FMA per warp instruction
+    } else {
+        const int iters = 1 << 13;
+        rc = time_kernel([&] { dmma_probe_kernel<1><<<blocks, threads>>>(d_out, iters, 1.0000001, 1e-9); }, &ms);
+        flops = (2.0 * 256.0 * 4 * (threads / 32) + 2.0 * 4 * threads) * (double)iters * blocks;
+    }
+    cudaFree(d_out);
+    if (rc) return rc;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    return 0;
+}
+
+extern "C" int tip_measure_red_f64(int64_t n_addr, int mode, double *gops)
+{
+    TIP_REQUIRE(gops != nullptr && n_addr >= 10 && (mode == 0 || mode == 1), "tip_measure_red_f64: bad arguments");
+    double *buf = nullptr;
+    TIP_CHECK_CUDA(cudaMalloc(&buf, (size_t)n_addr * 8));
+    TIP_CHECK_CUDA(cudaMemset(buf, 0, (size_t)n_addr * 8));
+    const int blocks = sm_count() * 8, threads = 256, iters = 2048;
+    double ms = 0;
+    int rc = time_kernel([&] { red_probe_kernel<<<blocks, threads>>>(buf, n_addr, mode, iters); }, &ms);
+    cudaFree(buf);
+    if (rc) return rc;
+    const double lanes = mode == 0 ? 32.0 : 30.0;
+    *gops = lanes / 32.0 * (double)blocks * threads * iters / (ms * 1e-3) / 1e9;
+    return 0;
+}

@@ -1,0 +1,210 @@
+"""Device-side state of one MMSBM model: packed link rows, theta, p, statistics - and the calls into
+libtip.so that advance it.  PyTorch owns the memory and the streams; every number is produced by the
+CUDA kernels behind the C ABI (include/tip.h).  There is no CPU path.
+
+    eng = EMEngine(P, K, device)                       # optionally group=torch.distributed group
+    eng.set_train_links(g1, g2, g3, n0, n1)            # this rank's link shard (ids in key slot order)
+    eng.set_params(theta, p)                           # numpy fp64, reference layouts
+    eng.em_iterations(n)                               # n x make_iteration (TIP.py:984-1043)
+    eng.loglik("train")                                # compute_likelihood (TIP.py:952-974)
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import dist as _dist
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class PackedLinks:
+    """Packed rows of one link set on the device (see include/tip.h)."""
+
+    def __init__(self, rows, n_rows, n_rows_r0, n_real, deg):
+        self.rows, self.n_rows, self.n_rows_r0, self.n_real, self.deg = rows, n_rows, n_rows_r0, n_real, deg
+
+
+class EMEngine:
+    def __init__(self, P: int, K: int, device=None, group=None, flags: int = _cabi.TIP_EM_DEFAULT):
+        if not torch.cuda.is_available():
+            raise _cabi.TipLibraryError("no CUDA device: trigenicinteractionpredictor_b200 has no CPU path")
+        self.lib = _cabi.load()
+        self.P, self.K = int(P), int(K)
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.group = group
+        self.flags = int(flags)
+        self.world = _dist.world_size(group)
+        self.n_stats = int(self.lib.tip_stats_len(self.P, self.K))
+        with torch.cuda.device(self.device):
+            self.theta = torch.empty(self.P * self.K, dtype=torch.float64, device=self.device)
+            self.p = torch.empty(2 * self.K ** 3, dtype=torch.float64, device=self.device)
+            self.stats = torch.zeros(self.n_stats, dtype=torch.float64, device=self.device)
+            self.ll_out = torch.zeros(1, dtype=torch.float64, device=self.device)
+            self.ll_ws = torch.empty(int(self.lib.tip_loglik_workspace_bytes()), dtype=torch.uint8, device=self.device)
+        self.train: PackedLinks | None = None
+        self.test: PackedLinks | None = None
+        self.test_ids = None      # (g1, g2, g3, labels) int32 tensors in test order
+        self.em_ws = None
+        self._graph = None
+        self._graph_key = None
+        self.launches = 0         # kernel launches issued by libtip on behalf of this engine
+
+    # ------------------------------------------------------------------ link sets
+    def _as_dev_i32(self, a):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=torch.int32).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
+
+    def pack(self, g1, g2, g3, n0, n1, want_deg=True) -> PackedLinks:
+        """tip_pack_rows: SoA -> rows ordered (rating, slot-a gene) in 32-row single-rating tiles."""
+        g1, g2, g3, n0, n1 = (self._as_dev_i32(x) for x in (g1, g2, g3, n0, n1))
+        L = int(g1.numel())
+        with torch.cuda.device(self.device):
+            nb = ctypes.c_size_t(0)
+            _cabi.check(self.lib.tip_pack_rows_workspace_bytes(L, ctypes.byref(nb)), "tip_pack_rows_workspace_bytes")
+            ws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+            rows = torch.empty((int(self.lib.tip_rows_capacity(L)), 4), dtype=torch.int32, device=self.device)
+            deg = torch.zeros(self.P, dtype=torch.int32, device=self.device) if want_deg else None
+            n_rows = ctypes.c_int64(0)
+            part = (ctypes.c_int64 * 3)()
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _cabi.check(self.lib.tip_pack_rows(_ptr(g1), _ptr(g2), _ptr(g3), _ptr(n0), _ptr(n1), L, self.P, _ptr(ws),
+                                               nb.value, _ptr(rows), ctypes.byref(n_rows), part, _ptr(deg),
+                                               ctypes.c_void_p(st)), "tip_pack_rows")
+            self.launches += 3
+            rows = rows[: n_rows.value].clone() if n_rows.value < rows.shape[0] else rows
+        return PackedLinks(rows, int(n_rows.value), int(part[0]), int(part[2]), deg)
+
+    def set_train_links(self, g1, g2, g3, n0, n1, global_deg=None):
+        """This rank's shard of the training links.  `deg` (distinct links per gene, TIP.py:986-994) is
+        summed over shards unless the caller supplies the global vector."""
+        self.train = self.pack(g1, g2, g3, n0, n1, want_deg=True)
+        if global_deg is not None:
+            self.train.deg = self._as_dev_i32(global_deg)
+        elif self.world > 1:
+            _dist.allreduce_sum_(self.train.deg, self.group)
+        with torch.cuda.device(self.device):
+            nb = ctypes.c_size_t(0)
+            _cabi.check(self.lib.tip_em_workspace_bytes(self.P, self.K, self.train.n_rows, self.flags, ctypes.byref(nb)),
+                        "tip_em_workspace_bytes")
+            self.em_ws = torch.empty(max(nb.value, 8), dtype=torch.uint8, device=self.device)
+            self.em_ws_bytes = nb.value
+        self._graph = None
+
+    def set_test_links(self, g1, g2, g3, n0, n1):
+        self.test = self.pack(g1, g2, g3, n0, n1, want_deg=False)
+        g1, g2, g3, n0 = (self._as_dev_i32(x) for x in (g1, g2, g3, n0))
+        labels = (n0 == 0).to(torch.int32)            # TIP.py:560-563: 0 if n0 else 1
+        self.test_ids = (g1, g2, g3, labels)
+
+    def degrees(self) -> np.ndarray:
+        return self.train.deg.cpu().numpy()
+
+    # ------------------------------------------------------------------ parameters
+    def set_params(self, theta, p):
+        th = torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float64).reshape(-1))
+        pp = torch.from_numpy(np.ascontiguousarray(p, dtype=np.float64).reshape(-1))
+        assert th.numel() == self.P * self.K and pp.numel() == 2 * self.K ** 3
+        self.theta.copy_(th, non_blocking=False)
+        self.p.copy_(pp, non_blocking=False)
+
+    def get_params(self):
+        return (self.theta.cpu().numpy().reshape(self.P, self.K),
+                self.p.cpu().numpy().reshape(self.K, self.K, self.K, 2))
+
+    # ------------------------------------------------------------------ EM
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def em_step(self):
+        """E-step statistics of this rank's rows into self.stats (no normalisation)."""
+        t = self.train
+        _cabi.check(self.lib.tip_em_step(self.P, self.K, _ptr(t.rows), t.n_rows, t.n_rows_r0, _ptr(self.theta),
+                                         _ptr(self.p), _ptr(self.stats), _ptr(self.em_ws), self.em_ws_bytes,
+                                         self.flags, self._stream()), "tip_em_step")
+        self.launches += 1 if (self.K <= 10 and not (self.flags & _cabi.TIP_EM_FORCE_GENERIC)) else 2
+
+    def normalise(self):
+        _cabi.check(self.lib.tip_normalise(self.P, self.K, _ptr(self.stats), _ptr(self.train.deg), _ptr(self.theta),
+                                           _ptr(self.p), self._stream()), "tip_normalise")
+        self.launches += 1
+
+    def em_iteration(self):
+        """One make_iteration: E-step, sum of statistics over link shards, M-step."""
+        self.em_step()
+        if self.world > 1:
+            _dist.allreduce_sum_(self.stats, self.group)
+        self.normalise()
+
+    def em_iterations(self, n: int, use_graph: bool = True):
+        """n iterations; the (E-step, allreduce, M-step) body is captured once in a CUDA graph and replayed
+        (an iteration at K=10 on 1e6 links is a few hundred microseconds, so launch latency matters)."""
+        if n <= 0:
+            return
+        if not use_graph or n < 3:
+            for _ in range(n):
+                self.em_iteration()
+            return
+        key = (self.train.rows.data_ptr(), self.train.n_rows, self.flags)
+        if self._graph is None or self._graph_key != key:
+            with torch.cuda.device(self.device):
+                self.em_iteration()                       # warm-up outside capture (sets func attributes, NCCL)
+                n -= 1
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                before = self.launches
+                with torch.cuda.graph(g):
+                    self.em_iteration()
+                self._graph_launches = self.launches - before
+                self.launches = before
+                self._graph, self._graph_key = g, key
+        for _ in range(n):
+            self._graph.replay()
+            self.launches += self._graph_launches
+
+    # ------------------------------------------------------------------ likelihood / scoring / metrics
+    def loglik(self, which: str = "train") -> float:
+        links = self.train if which == "train" else self.test
+        if links is None:
+            raise ValueError("no %s links set" % which)
+        _cabi.check(self.lib.tip_loglik(self.P, self.K, _ptr(links.rows), links.n_rows, _ptr(self.theta), _ptr(self.p),
+                                        _ptr(self.ll_out), _ptr(self.ll_ws), self._stream()), "tip_loglik")
+        self.launches += 1
+        if self.world > 1 and which == "train":
+            _dist.allreduce_sum_(self.ll_out, self.group)
+        return float(self.ll_out.item())
+
+    def step_loglik(self) -> float:
+        """log-likelihood by-product of the last E-step (of the parameters that step started from)."""
+        return float(self.stats[-1].item())
+
+    def scores(self) -> torch.Tensor:
+        g1, g2, g3, _ = self.test_ids
+        T = int(g1.numel())
+        out = torch.empty(T, dtype=torch.float64, device=self.device)
+        _cabi.check(self.lib.tip_score(self.P, self.K, _ptr(g1), _ptr(g2), _ptr(g3), T, _ptr(self.theta), _ptr(self.p),
+                                       _ptr(out), self._stream()), "tip_score")
+        self.launches += 1
+        return out
+
+    def metric_counts(self, scores: torch.Tensor, positives_number: int) -> dict:
+        """Integer ingredients of calculate_metrics (TIP.py:583-637); ratios are formed by the caller."""
+        labels = self.test_ids[3]
+        T = int(scores.numel())
+        nb = ctypes.c_size_t(0)
+        _cabi.check(self.lib.tip_metrics_workspace_bytes(T, ctypes.byref(nb)), "tip_metrics_workspace_bytes")
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+        out = torch.zeros(8, dtype=torch.int64, device=self.device)
+        _cabi.check(self.lib.tip_metrics(_ptr(scores), _ptr(labels), T, int(positives_number), _ptr(ws), nb.value,
+                                         _ptr(out), self._stream()), "tip_metrics")
+        self.launches += 5
+        o = out.cpu().numpy()
+        cut = float(np.array([o[7]], dtype=np.int64).view(np.float64)[0])
+        return {"wins": int(o[0]), "n_pos": int(o[1]), "n_neg": int(o[2]), "tp": int(o[3]), "fp": int(o[4]),
+                "fn": int(o[5]), "tn": int(o[6]), "cut_value": cut}
