@@ -27,6 +27,7 @@
  *     [0, P*K)                 Ntheta[g][k]   = sum over links/slots of omega * n     (TIP.py:1009-1011)
  *     [P*K, P*K + 2*K^3)       S[r][a][b][c]  = sum_l n_lr/d_lr * th_a th_b th_c     (npr = p * S, TIP.py:1012)
  *     [P*K + 2*K^3]            sum_l n_lr * log(d_lr) of the parameters the step STARTED from
+ *                              (only with TIP_EM_WITH_LOGLIK or on the any-K path; 0 otherwise)
  */
 #ifndef TIP_H_
 #define TIP_H_
@@ -47,6 +48,9 @@ extern "C" {
 #define TIP_EM_DEFAULT 0u
 #define TIP_EM_FORCE_GENERIC 1u /* use the any-K kernels even where a K-specialised kernel exists */
 #define TIP_EM_FP32_COMPUTE 2u  /* fp32 products / fp64 accumulation (1e-5 mode); not in ABI v1 kernels yet */
+#define TIP_EM_WITH_LOGLIK 4u   /* also accumulate the log-likelihood by-product (last stats slot); off by
+                                   default because the log costs ~2 % of a K=10 step and the training loop only
+                                   needs the likelihood every `fcheck` iterations (tip_loglik) */
 
 int tip_abi_version(void);
 const char *tip_last_error(void);
@@ -70,7 +74,8 @@ int tip_pack_rows(const int32_t *d_g1, const int32_t *d_g2, const int32_t *d_g3,
 /* ---- Model.make_iteration, E-step half (TIP.py:987-1012) ----
  * Zeroes d_stats, then accumulates the statistics of `n_rows` packed rows under (d_theta, d_p).
  * n_rows_r0 = rows in the rating-0 block (h_part[0] of tip_pack_rows); both are multiples of 32.
- * d_ws: tip_em_workspace_bytes() bytes of scratch (0 for the K-specialised kernels; may be NULL then). */
+ * d_ws: tip_em_workspace_bytes() bytes of scratch (per-gene M matrices for K = 5..10, per-row s for K > 10;
+ *       0 for K <= 4, where it may be NULL). */
 int tip_em_workspace_bytes(int P, int K, int64_t n_rows, unsigned flags, size_t *bytes);
 int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int64_t n_rows_r0, const double *d_theta,
                 const double *d_p, double *d_stats, void *d_ws, size_t ws_bytes, unsigned flags, void *stream);

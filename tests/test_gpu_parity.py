@@ -67,7 +67,9 @@ def test_em_trace_matches_reference(torch_cuda, K, flags):
     same = sum(1 for r, k in zip(res, tr["result_keys"].tolist()) if r[1] == k)
     assert same >= len(res) - 4, "sorted test table differs beyond near-tie swaps"
     met = m.calculate_metrics()
-    assert met[3] == pytest.approx(tr["metrics"][3], abs=1e-6)          # AUC
+    # K=1 is degenerate: theta == 1 - O(eps), every score equals p[0][0][0][1] to ~1e-10, so the pair
+    # order (and the AUC) is decided at rounding level; the 1e-6 AUC gate applies to K >= 2
+    assert met[3] == pytest.approx(tr["metrics"][3], abs=1e-6 if K > 1 else 1e-3)   # AUC
     np.testing.assert_allclose(met[:3], tr["metrics"][:3], atol=1e-2)   # rank-cut counts may move by one on a tie
     # single-triplet prediction by id strings and by gene names (TIP.py:541-545)
     key = next(iter(m.test_links)).split("_")
@@ -152,7 +154,7 @@ def test_em_step_vs_oracle_all_k(torch_cuda, K):
     ent, enp, deg = orc.em_step_np(theta, pr, g.astype(np.int64), cnt, return_stats=True)
     ll = orc.loglik_np(theta, pr, g.astype(np.int64), cnt)
     th1, pr1 = orc.normalise_np(ent, enp, deg)
-    for flags in ([0, 1] if K <= 10 else [0]):
+    for flags in ([4, 1, 0] if K <= 10 else [0]):      # 4 = TIP_EM_WITH_LOGLIK, 1 = TIP_EM_FORCE_GENERIC
         eng = EMEngine(P, K, flags=flags)
         eng.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
         eng.set_params(theta, pr)
@@ -163,7 +165,10 @@ def test_em_step_vs_oracle_all_k(torch_cuda, K):
         npr = pr * np.moveaxis(S, 0, -1)
         assert _relerr(nth, ent) < 1e-11, "Ntheta K=%d flags=%d" % (K, flags)
         assert _relerr(npr, np.maximum(enp, 1e-300)) < 1e-11, "Np K=%d flags=%d" % (K, flags)
-        assert st[-1] == pytest.approx(ll, rel=1e-12)
+        if flags != 0 or K > 10:
+            assert st[-1] == pytest.approx(ll, rel=1e-12)      # by-product of the E-step
+        else:
+            assert st[-1] == 0.0                                # not requested on the specialised path
         assert eng.loglik("train") == pytest.approx(ll, rel=1e-12)
         eng.normalise()
         th, p = eng.get_params()
@@ -265,7 +270,7 @@ def test_full_size_properties_cfg2(torch_cuda):
     pr = rng.random((K, K, K, 2))
     pr /= pr.sum(axis=3, keepdims=True)
     outs = []
-    for flags in (0, 1):
+    for flags in (4, 1):                               # specialised kernel (+loglik by-product), any-K kernels
         eng = EMEngine(P, K, flags=flags)
         eng.set_train_links(g1, g2, g3, 1 - lab, lab)
         assert eng.train.n_real == L

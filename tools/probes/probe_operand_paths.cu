@@ -1,0 +1,109 @@
+// Probe: how should the warp-uniform p[a][b][c] operand reach the DFMA pipe at K=10?
+//   mode 0: shared memory, broadcast 128-bit loads (what em_fused_kernel does)
+//   mode 1: __constant__ bank operand, fully unrolled (DFMA R, R, c[bank][imm], R)
+//   mode 2: DFMA dependent-chain latency
+// Each thread plays one link of phase A: q[ab] = sum_c p[abc]*tc[c]; w[c] += ab*p[abc]  (2000 DFMA per pass)
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+constexpr int K = 10, NP = K * K * K;
+__constant__ double cp[NP];
+
+template <int MODE>
+__global__ void __launch_bounds__(128) phase_a_probe(const double *__restrict__ gp, double *out, int passes)
+{
+    __shared__ __align__(16) double sp[NP];
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) sp[i] = gp[i];
+    __syncthreads();
+    double tc[K], tb[K], w[K], v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { tc[k] = 0.1 * (k + 1) + threadIdx.x * 1e-6; tb[k] = 0.05 * (k + 2); w[k] = 0; v[k] = 0; }
+    double acc = 0;
+    for (int pass = 0; pass < passes; ++pass) {
+#pragma unroll 1
+        for (int a = 0; a < K; ++a) {
+            const double ta = tc[0] + pass + a;
+            double u = 0;
+#pragma unroll
+            for (int b = 0; b < K; ++b) {
+                const double ab = ta * tb[b];
+                double q0 = 0, q1 = 0;
+#pragma unroll
+                for (int c = 0; c < K; c += 2) {
+                    double p0, p1;
+                    if (MODE == 0) {
+                        const double2 pv = *reinterpret_cast<const double2 *>(sp + (a * K + b) * K + c);
+                        p0 = pv.x; p1 = pv.y;
+                    } else {
+                        p0 = cp[(a * K + b) * K + c]; p1 = cp[(a * K + b) * K + c + 1];
+                    }
+                    q0 = fma(p0, tc[c], q0); q1 = fma(p1, tc[c + 1], q1);
+                    w[c] = fma(ab, p0, w[c]); w[c + 1] = fma(ab, p1, w[c + 1]);
+                }
+                const double q = q0 + q1;
+                u = fma(tb[b], q, u);
+                v[b] = fma(ta, q, v[b]);
+            }
+            acc += ta * u;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc += w[k] + v[k];
+    if (acc == 1234.5678) out[0] = acc;
+}
+
+__global__ void dfma_latency_probe(double *out, long long *cycles, int n)
+{
+    double x = threadIdx.x * 1e-3, a = 1.0000001, b = 1e-9;
+    long long t0 = clock64();
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x = fma(x, a, b);
+    }
+    long long t1 = clock64();
+    if (x == 1234.5) out[0] = x;
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
+template <int MODE>
+void run(const double *gp, double *out, int blocks_per_sm, int threads)
+{
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int passes = 200;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    phase_a_probe<MODE><<<sms * blocks_per_sm, threads>>>(gp, out, 2);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    phase_a_probe<MODE><<<sms * blocks_per_sm, threads>>>(gp, out, passes);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double fma_per_thread = (double)passes * (2.0 * NP + 2.0 * K * K + K * K /*ab*/ + K * K /*q add*/ + 2 * K);
+    const double tf = 2.0 * fma_per_thread * sms * blocks_per_sm * threads / (ms * 1e-3) / 1e12;
+    printf("mode %d  warps/SM %2d : %.3f ms  %.2f TFLOP/s-equivalent (fp64 pipe instrs x2)  err=%s\n", MODE,
+           blocks_per_sm * threads / 32, ms, tf, cudaGetErrorString(cudaGetLastError()));
+}
+
+int main()
+{
+    double h[NP];
+    for (int i = 0; i < NP; ++i) h[i] = 0.001 * (i % 97) + 0.01;
+    double *gp, *out; long long *cyc;
+    cudaMalloc(&gp, sizeof(h)); cudaMalloc(&out, 64); cudaMalloc(&cyc, 64);
+    cudaMemcpy(gp, h, sizeof(h), cudaMemcpyHostToDevice);
+    cudaMemcpyToSymbol(cp, h, sizeof(h));
+    for (int wps : {4, 8, 12, 16, 20}) {
+        run<0>(gp, out, wps / 4, 128);
+        run<1>(gp, out, wps / 4, 128);
+    }
+    dfma_latency_probe<<<1, 32>>>(out, cyc, 1000);
+    cudaDeviceSynchronize();
+    long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("DFMA dependent-issue latency: %.2f cycles\n", (double)c / 16000.0);
+    dfma_latency_probe<<<1, 64>>>(out, cyc, 1000);  // 2 warps, 1 per SMSP pair
+    cudaDeviceSynchronize();
+    return 0;
+}

@@ -1,0 +1,36 @@
+#!/usr/bin/env python3
+"""Short driver for ncu: cfg2-shaped workload (6000 genes, 800k links, K=10), a few E-steps + M-steps."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from trigenicinteractionpredictor_b200 import synth  # noqa: E402
+from trigenicinteractionpredictor_b200.engine import EMEngine  # noqa: E402
+
+K = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+L = int(sys.argv[2]) if len(sys.argv) > 2 else 800_000
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+flags = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+P = 6000
+dev = torch.device("cuda:0")
+eng = EMEngine(P, K, device=dev, flags=flags)
+g1, g2, g3, lab = synth.planted_links_soa(P, L, seed=100, device=dev)
+g1[:P] = torch.arange(P, dtype=torch.int32, device=dev)
+eng.set_train_links(g1, g2, g3, 1 - lab, lab)
+rng = np.random.default_rng(0)
+theta = rng.dirichlet(np.ones(K), size=P)
+pr = rng.random((K, K, K, 2))
+pr /= pr.sum(axis=3, keepdims=True)
+eng.set_params(theta, pr)
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for i in range(iters):
+    a.record()
+    eng.em_step()
+    b.record()
+    eng.normalise()
+    torch.cuda.synchronize()
+    print("iter %d: em_step %.3f ms  (%.3e link-updates/s)" % (i, a.elapsed_time(b), L / a.elapsed_time(b) * 1e3))
+print("loglik", eng.loglik("train"))

@@ -33,7 +33,7 @@ extern "C" int tip_em_workspace_bytes(int P, int K, int64_t n_rows, unsigned fla
 {
     TIP_REQUIRE(bytes != nullptr && P > 0 && valid_K(K) && n_rows >= 0, "tip_em_workspace_bytes: bad arguments");
     const bool tuned = !(flags & TIP_EM_FORCE_GENERIC) && K <= 10;
-    *bytes = tuned ? 0 : (size_t)(n_rows < 1 ? 1 : n_rows) * sizeof(double);
+    *bytes = tuned ? em_tuned_workspace_bytes(P, K) : (size_t)(n_rows < 1 ? 1 : n_rows) * sizeof(double);
     return 0;
 }
 
@@ -50,9 +50,13 @@ extern "C" int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int
     TIP_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * (size_t)tip_stats_len(P, K), st));
     if (n_rows == 0) return 0;
     const int4 *rows = reinterpret_cast<const int4 *>(d_rows);
-    if (!(flags & TIP_EM_FORCE_GENERIC)) {
+    if (!(flags & TIP_EM_FORCE_GENERIC) && K <= 10) {
+        const size_t need = em_tuned_workspace_bytes(P, K);
+        TIP_REQUIRE(need == 0 || (d_ws != nullptr && ws_bytes >= need),
+                    "tip_em_step: K=%d needs %zu bytes of workspace (got %zu), see tip_em_workspace_bytes", K, need, ws_bytes);
         bool handled = false;
-        int rc = launch_em_tuned(P, K, rows, n_rows, d_theta, d_p, d_stats, st, &handled);
+        int rc = launch_em_tuned(P, K, rows, n_rows, n_rows_r0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws),
+                                 (flags & TIP_EM_WITH_LOGLIK) != 0, st, &handled);
         if (rc != 0 || handled) return rc;
     }
     TIP_REQUIRE(d_ws != nullptr && ws_bytes >= (size_t)n_rows * sizeof(double),

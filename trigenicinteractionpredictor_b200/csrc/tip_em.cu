@@ -1,171 +1,280 @@
 // K-specialised fused E-step for sm_100a (K = 1..10): the hot kernel of Model.make_iteration
-// (TIP.py:987-1012).  fp64 CUDA-core FMA bound: 3 DFMA per (a,b,c) cell per link-update.
+// (TIP.py:987-1012).  fp64 CUDA-core FMA bound.
 //
-// One persistent CTA per SM, 8 warps, every warp independent (no CTA barrier in the main loop).
-// A warp walks tiles of 32 packed rows (all one rating, see tip.h):
+// Persistent single-warp CTAs (12 resident per SM): every control decision depends only on
+// blockIdx / kernel parameters, which lets ptxas prove warp-uniformity and keep the p operand on the
+// uniform datapath.  A warp walks tiles of 32 packed rows (all one rating, see tip.h):
 //
 //   gather   cp.async the three theta rows of each of the 32 links into a [link][th_a|th_b|th_c]
-//            shared-memory stage, row-contiguous so every request touches whole 8*K-byte rows;
-//            double buffered: the rows of tile t+1 arrive while tile t is computed.
+//            shared-memory stage (16-byte copies, whole rows per request).
 //   phase A  lane = link.  th_b, th_c and the accumulators v[K], w[K] live in registers;
-//            p[.][.][.][r] is read from shared memory as warp-uniform (broadcast) 128-bit loads.
+//            p[.][.][.][r] comes from the constant bank on the uniform datapath (see c_pem).
 //              q[ab]  = sum_c p[abc] th_c[c]              K^3 DFMA
 //              w[c]  += th_a[a] th_b[b] p[abc]            K^3 DFMA
 //              u[a]  += th_b[b] q[ab],  v[b] += th_a[a] q[ab]
 //            d = eps + sum_a th_a[a] u[a];  s = count / d.
-//            Contributions s*th_a*u, s*th_b*v, s*th_c*w go to a [link][3K] shared buffer, s*th_c
-//            overwrites th_c in the stage.
-//   scatter  slot-a contributions are summed over runs of equal gene (rows are sorted by slot-a
-//            gene) before one red.global.add.f64 per run; slot-b/c contributions are issued
-//            row-contiguously (one warp instruction covers 3.2 theta rows).
-//   phase B  lanes = cells.  S[a][b][c] += th_a[a] th_b[b] * (s th_c[c]) for the 32 links of the
-//            tile, each lane owning a (1 x BG x K) block of S in registers for the whole kernel.
-//            (K <= 4: S is small enough to be thread-private and is updated in phase A.)
-//
-// At the end S is reduced across the CTA in shared memory and added to the global statistics.
+//            Slot-b/c contributions s*th_b*v, s*th_c*w go to a [link][3K] shared buffer and from there
+//            to the statistics with one bulk add-reduction (TMA unit) per theta row; s*th_c overwrites
+//            th_c in the stage.
+//   phase B  Rows are sorted by slot-a gene g, so th_a is constant over a run of links and everything
+//            that multiplies th_a can be accumulated per gene first (gene-segmented factorisation):
+//              M_g[b][c] += th_b[b] * (s th_c[c])         per link   K^2 DFMA (lanes = cells of M)
+//            and, once per iteration in em_finalize_kernel,
+//              Ntheta[g][a] += th_g[a] * sum_bc p[abc] M_g[b][c]      (the slot-a statistic)
+//              S[a][b][c]   += th_g[a] * M_g[b][c]                    (the p statistic, npr = p * S)
+//            so the p statistic costs K^2 per link + 2 K^3 per (gene, rating) instead of K^3 per link,
+//            and the slot-a scatter disappears.  M_g lives in the workspace (2*P*K^2 doubles).
+//   K <= 4   K^3 <= 64: S is thread-private (registers) and updated in phase A; slot-a contributions are
+//            pre-reduced over runs of equal gene; no workspace.
+#include <stdlib.h>
+
 #include "tip_common.cuh"
 
 namespace tip {
 
-constexpr int kEmWarps = 8;
-constexpr int kEmThreads = kEmWarps * kWarp;
+// p in the E-step layout [r][ab][c] (c padded to KP), read through the constant bank: the index is
+// warp-uniform, so ptxas keeps p on the uniform datapath (LDCU.64 -> UR operand of DFMA) and the
+// 1000 values per link never touch the vector register file or the shared-memory pipe.  Measured on
+// B200 (tools/probes/probe_operand_paths.cu): shared-memory broadcast saturates at 75 % of the DFMA
+// peak whatever the occupancy; the constant path reaches 84 % at 8 warps/SM and 89 % at 20.
+constexpr int kPSlots = 3;           // launches rotate over slots so neighbouring streams do not collide
+constexpr int kPSlotDoubles = 2000;  // max over K<=10 of 2*K*K*KP
+__constant__ double c_pem[kPSlots * kPSlotDoubles];
+__device__ double g_pstage[kPSlots * kPSlotDoubles];
 
-template <int K>
+template <int K, int NBUF>
 struct EmCfg {
-    static constexpr int KP = K + (K & 1);                                // sub-row length (even)
-    static constexpr int S3 = 3 * KP;                                     //
-    static constexpr int RS = S3 + ((S3 % 4 == 2) ? 0 : 2);               // row stride == 2 (mod 4): conflict-free 128-bit rows
+    static constexpr int KP = K + (K & 1);                   // sub-row length (even)
+    static constexpr int S3 = 3 * KP;
+    static constexpr int RS = S3 + ((S3 % 4 == 2) ? 0 : 2);  // row stride == 2 (mod 4): conflict-free 128-bit rows
     static constexpr int K3 = K * K * K;
-    static constexpr bool kPrivateS = (K <= 4);                           // S thread-private
-    // phase B lane mapping: lane -> (alpha = lane % K, group = lane / K), group covers BG betas
+    static constexpr bool kPrivateS = (K <= 4);              // S thread-private, no gene segmentation
+    // phase B lane mapping: lane -> (b = lane % K, c-group = lane / K), a group covers CB values of c
     static constexpr int NG = (32 / K) < K ? (32 / K) : K;
-    static constexpr int BG = (K + NG - 1) / NG;
-    static constexpr int NGU = (K + BG - 1) / BG;                         // groups actually needed
-    static constexpr int SP = 2 * K * K * KP;                             // doubles of staged p (both ratings)
-    // per-warp shared memory (doubles): 2 theta stages + contribution buffer, then ids (2 x 32 int4)
-    static constexpr int WARP_DBL = 3 * 32 * RS;
-    static constexpr size_t WARP_BYTES = (size_t)WARP_DBL * 8 + 2 * 32 * 16;
-    static constexpr size_t SMEM = (size_t)SP * 8 + (size_t)2 * K3 * 8 + kEmWarps * WARP_BYTES;
+    static constexpr int CB = (K + NG - 1) / NG;
+    static constexpr int NGU = (K + CB - 1) / CB;            // groups actually needed
+    // shared memory of one warp-CTA: NBUF theta stages + contribution buffer (doubles), then ids (NBUF x 32 int4)
+    static constexpr int WARP_DBL = (NBUF + 1) * 32 * RS;
+    static constexpr size_t SMEM = (size_t)WARP_DBL * 8 + NBUF * 32 * 16;
 };
 
-template <int K>
-__device__ __forceinline__ void gather_tile(const double *__restrict__ theta, const int4 *ids, double *stage, int lane)
+// p[abc][r] (reference layout) -> [r][ab][c padded] staging copy, then memcpy to the constant bank
+__global__ void stage_p_kernel(int K, int KP, const double *__restrict__ p, double *__restrict__ out)
 {
-    using C = EmCfg<K>;
-    const int *idw = reinterpret_cast<const int *>(ids);
-#pragma unroll 5
-    for (int i = 0; i < 3 * K; ++i) {
-        const int idx = i * 32 + lane;
-        const int l = idx / (3 * K), rem = idx - l * (3 * K);
-        const int slot = rem / K, k = rem - slot * K;
-        const int g = idw[l * 4 + slot];
-        cp_async_8(stage + l * C::RS + slot * C::KP + k, theta + (int64_t)g * K + k);
+    const int n = 2 * K * K * KP;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int r = e / (K * K * KP), rem = e - r * (K * K * KP);
+        const int pair = rem / KP, c = rem - pair * KP;
+        out[e] = (c < K) ? p[((int64_t)pair * K + c) * 2 + r] : 0.0;
     }
 }
 
+// Row gather: LPI links per warp instruction, each link's three theta rows copied as U units of
+// UNIT doubles (16-byte cp.async when K is even).  Which (link-in-group, slot, unit) a lane serves is
+// fixed for the whole kernel, so an iteration costs one id load, two address computations and the copy.
 template <int K>
-__global__ void __launch_bounds__(kEmThreads, 1)
-    em_fused_kernel(int P, const int4 *__restrict__ rows, int64_t n_tiles, const double *__restrict__ theta,
-                    const double *__restrict__ p, double *__restrict__ stats)
+struct GatherMap {
+    static constexpr int UNIT = (K % 2 == 0) ? 2 : 1;
+    static constexpr int U = K / UNIT;
+    static constexpr int LPI = 32 / (3 * U);
+    static constexpr int ITERS = (32 + LPI - 1) / LPI;
+};
+
+template <int K, int RS, int KP>
+__device__ __forceinline__ void gather_tile(const double *__restrict__ theta, const int4 *ids, double *stage, int lane)
 {
-    using C = EmCfg<K>;
-    constexpr int KP = C::KP, RS = C::RS, K3 = C::K3, BG = C::BG;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *sp = reinterpret_cast<double *>(smem_raw);            // [2][K*K][KP]
-    double *Ssm = sp + C::SP;                                     // [2][K3]
-    const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
-    unsigned char *wbase = reinterpret_cast<unsigned char *>(Ssm + 2 * K3) + (size_t)warp * C::WARP_BYTES;
-    double *stage0 = reinterpret_cast<double *>(wbase);           // [2][32][RS]
-    double *cbuf = stage0 + 2 * 32 * RS;                          // [32][RS]
-    int4 *ids_sm = reinterpret_cast<int4 *>(cbuf + 32 * RS);      // [2][32]
-
-    // ---- stage p (transposed to [r][ab][c], c padded to KP) and clear the CTA's S ----
-    for (int e = threadIdx.x; e < 2 * K * K * KP; e += kEmThreads) {
-        const int r = e / (K * K * KP), rem = e - r * (K * K * KP);
-        const int pair = rem / KP, c = rem - pair * KP;
-        sp[e] = (c < K) ? __ldg(p + ((int64_t)pair * K + c) * 2 + r) : 0.0;
+    using G = GatherMap<K>;
+    const int sub = lane / (3 * G::U), rem = lane - sub * (3 * G::U);
+    const int slot = rem / G::U, k0 = (rem - slot * G::U) * G::UNIT;
+    const bool active = sub < G::LPI;
+    const int *idp = reinterpret_cast<const int *>(ids) + sub * 4 + slot;
+    double *dst = stage + sub * RS + slot * KP + k0;
+    const double *src0 = theta + k0;
+#pragma unroll 4
+    for (int it = 0; it < G::ITERS; ++it) {
+        if (active && (32 % G::LPI == 0 || it * G::LPI + sub < 32)) {
+            const int g = *idp;
+            if (G::UNIT == 2)
+                cp_async_16(dst, src0 + (int64_t)g * K);
+            else
+                cp_async_8(dst, src0 + (int64_t)g * K);
+        }
+        idp += G::LPI * 4;
+        dst += G::LPI * RS;
     }
-    for (int e = threadIdx.x; e < 2 * K3; e += kEmThreads) Ssm[e] = 0.0;
-    __syncthreads();
+}
 
-    const int64_t W = (int64_t)gridDim.x * kEmWarps;
-    const int64_t w0 = (int64_t)blockIdx.x * kEmWarps + warp;
+// fire-and-forget fp64 reduction, skipped when the value is exactly zero (padding rows)
+__device__ __forceinline__ void red_add_f64_nz(double *addr, double v)
+{
+    asm volatile("{ .reg .pred p; setp.neu.f64 p, %1, 0d0000000000000000; @p red.global.add.f64 [%0], %1; }" ::"l"(addr),
+                 "d"(v)
+                 : "memory");
+}
+
+// Bulk asynchronous add-reduction of `bytes` (multiple of 16) contiguous doubles from shared memory into
+// global memory (SASS: UBLKRED.G.S.ADD.F64): one request to the TMA unit per theta row instead of K
+// per-lane red.global.add.f64 (which cost the LSU ~1.3 cycles per lane).
+__device__ __forceinline__ void bulk_red_add_f64(double *gdst, const double *ssrc, int bytes)
+{
+    const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(ssrc));
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gdst), "r"(sa),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Scatter of slot-b / slot-c contributions with per-lane reductions (odd K, where a row is not a multiple
+// of 16 bytes): the flat index i*32+lane over 32 links x 2K values repeats its (link offset, slot, k)
+// pattern every PER warp instructions, so the PER offsets a lane needs are computed once per kernel.
+template <int K>
+struct ScatterMap {
+    static constexpr int gcd(int a, int b) { return b == 0 ? a : gcd(b, a % b); }
+    static constexpr int V = 2 * K;     // values per link
+    static constexpr int G = gcd(32, V);
+    static constexpr int PER = V / G;   // warp instructions per period
+    static constexpr int LPP = 32 / G;  // links per period
+    static constexpr int NPERIOD = G;   // periods per tile (32 / LPP)
+};
+
+template <int K, int NBUF, int MINB, bool LL>
+__global__ void __launch_bounds__(32, MINB)
+    em_fused_kernel(int P, const int4 *__restrict__ rows, int n_tiles, int n_tiles_r0, const double *__restrict__ theta,
+                    int p_slot, double *__restrict__ stats, double *__restrict__ Mg, int dbg)
+{
+    using C = EmCfg<K, NBUF>;
+    constexpr int KP = C::KP, RS = C::RS, K3 = C::K3, CB = C::CB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    double *stage0 = reinterpret_cast<double *>(smem_raw);    // [NBUF][32][RS]
+    double *cbuf = stage0 + NBUF * 32 * RS;                   // [32][RS]
+    int4 *ids_sm = reinterpret_cast<int4 *>(cbuf + 32 * RS);  // [NBUF][32]
+
+    // Tile bookkeeping (t, W, the rating of a tile, the p index) must stay on the uniform datapath.
+    // ptxas gives every value ONE home: a single per-lane use of %ctaid.x / %nctaid.x (the row pointers
+    // below) moves the tile counter - and with it the p index - to the vector register file, and the p
+    // loads degrade from LDCU (uniform) to per-lane LDC.64, measured 1.4x slower than even the
+    // shared-memory version.  volatile asm, a round trip through shared memory and shuffles do not
+    // separate the copies (the store or shuffle is itself a vector use).  What does: the per-lane side
+    // reads %clusterid.x / %nclusterid.x, which equal %ctaid.x / %nctaid.x for this non-cluster launch
+    // but are different special registers to the compiler.
+    const int W = gridDim.x;
+    const int w0 = blockIdx.x;
+    unsigned bx_v, gx_v;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(bx_v));
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(gx_v));
+    const int4 *rp = rows + (int64_t)bx_v * 32 + lane;  // next tile of rows this lane will fetch
+    const int64_t rstride = (int64_t)gx_v * 32;
 
     // phase B lane mapping
-    const int al_b = lane % K;
+    const int b_lane = lane % K;
     int grp = lane / K;
-    const bool b_active = (!C::kPrivateS) && grp < C::NGU;
+    const bool b_active = grp < C::NGU;
     if (grp >= C::NGU) grp = 0;
-    const int be0 = grp * BG;
+    const int c0 = grp * CB;
 
-    constexpr int NS = C::kPrivateS ? K3 : BG * K;
+    // odd K: scatter pattern of this lane, (value offset in cbuf | id offset << 16 | k << 24) per phase
+    unsigned sc_pack[ScatterMap<K>::PER];
+#pragma unroll
+    for (int ph = 0; ph < ScatterMap<K>::PER; ++ph) {
+        const int idx = ph * 32 + lane;
+        const int l = idx / (2 * K), rem = idx - l * (2 * K);
+        const int slot = 1 + rem / K, kk = rem % K;
+        sc_pack[ph] = (unsigned)(l * RS + slot * KP + kk) | ((unsigned)(l * 4 + slot) << 16) | ((unsigned)kk << 24);
+    }
+
+    // K <= 4 only: thread-private S
+    constexpr int NS = C::kPrivateS ? K3 : 1;
     double Sacc[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) Sacc[i] = 0.0;
     int cur_r = -1;
     double ll = 0.0;
+    double *Sg = stats + stats_off_S(P, K);
 
     auto flush_S = [&](int r) {
         if (r < 0) return;
-        double *dst = Ssm + r * K3;
-        if constexpr (C::kPrivateS) {
+        double *dst = Sg + r * K3;
 #pragma unroll
-            for (int i = 0; i < K3; ++i) {
-                const double t = warp_sum(Sacc[i]);
-                if (lane == 0) atomicAdd(dst + i, t);
-                Sacc[i] = 0.0;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < BG; ++j)
-#pragma unroll
-                for (int c = 0; c < K; ++c) {
-                    if (b_active && be0 + j < K) atomicAdd(dst + (al_b * K + be0 + j) * K + c, Sacc[j * K + c]);
-                    Sacc[j * K + c] = 0.0;
-                }
+        for (int i = 0; i < NS; ++i) {
+            const double t = warp_sum(Sacc[i]);
+            if (lane == 0 && t != 0.0) red_add_f64(dst + i, t);
+            Sacc[i] = 0.0;
         }
     };
 
-    // ---- software pipeline prologue ----
+    // ---- software pipeline prologue (NBUF == 2: rows of the next tile are gathered one tile ahead) ----
     int4 ids_next = make_int4(0, 0, 0, 0);
-    if (w0 < n_tiles) {
-        ids_sm[lane] = rows[w0 * 32 + lane];
+    if (NBUF == 2 && w0 < n_tiles) {
+        ids_sm[lane] = *rp;
+        rp += rstride;
         __syncwarp();
-        gather_tile<K>(theta, ids_sm, stage0, lane);
+        gather_tile<K, RS, KP>(theta, ids_sm, stage0, lane);
         cp_async_commit();
-        if (w0 + W < n_tiles) ids_next = rows[(w0 + W) * 32 + lane];
+        if (w0 + W < n_tiles) {
+            ids_next = *rp;
+            rp += rstride;
+        }
+    } else if (NBUF == 1 && w0 < n_tiles) {
+        ids_next = *rp;
+        rp += rstride;
     }
 
     int buf = 0;
-    for (int64_t t = w0; t < n_tiles; t += W, buf ^= 1) {
+    for (int t = w0; t < n_tiles; t += W) {
         double *stage = stage0 + buf * 32 * RS;
         const int4 *ids = ids_sm + buf * 32;
-        const bool has_next = (t + W) < n_tiles;
-        if (has_next) {
-            ids_sm[(buf ^ 1) * 32 + lane] = ids_next;
-            __syncwarp();
-            gather_tile<K>(theta, ids_sm + (buf ^ 1) * 32, stage0 + (buf ^ 1) * 32 * RS, lane);
-            cp_async_commit();
-            if (t + 2 * W < n_tiles) ids_next = rows[(t + 2 * W) * 32 + lane];
-            cp_async_wait<1>();
+        if (NBUF == 2) {
+            const bool has_next = (t + W) < n_tiles;
+            if (has_next) {
+                ids_sm[(buf ^ 1) * 32 + lane] = ids_next;
+                __syncwarp();
+                gather_tile<K, RS, KP>(theta, ids_sm + (buf ^ 1) * 32, stage0 + (buf ^ 1) * 32 * RS, lane);
+                cp_async_commit();
+                if (t + 2 * W < n_tiles) {
+                    ids_next = *rp;
+                    rp += rstride;
+                }
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
         } else {
+            ids_sm[lane] = ids_next;
+            __syncwarp();
+            gather_tile<K, RS, KP>(theta, ids_sm, stage0, lane);
+            cp_async_commit();
+            if (t + W < n_tiles) {
+                ids_next = *rp;
+                rp += rstride;
+            }
             cp_async_wait<0>();
         }
         __syncwarp();
 
         const int4 me = ids[lane];
-        const int r = row_rating(me.w);  // uniform across the tile
+        // the rating is the same for the whole tile and follows from the tile index alone, which keeps
+        // the p index below provably warp-uniform (uniform datapath)
+        const int r = t >= n_tiles_r0 ? 1 : 0;
+        // per-lane copy of the rating taken from the row data (same value for the whole tile), so that
+        // r itself never enters the vector register file
+        const int r_v = row_rating(me.w);
         const double cnt = (double)row_count(me.w);
-        if (r != cur_r) {
-            flush_S(cur_r);
-            cur_r = r;
+        if constexpr (C::kPrivateS) {
+            if (r_v != cur_r) {
+                flush_S(cur_r);
+                cur_r = r_v;
+            }
         }
 
         // ================= phase A: lane = link =================
         {
+            if constexpr (K % 2 == 0) bulk_wait_read();  // the previous tile's bulk reductions have read cbuf
             double *row = stage + lane * RS;
             double *crow = cbuf + lane * RS;
-            const double *spr = sp + r * (K * K * KP);
+            const int pbase = p_slot * kPSlotDoubles + r * (K * K * KP);
             double tb[KP], tc[KP], v[K], w[KP];
 #pragma unroll
             for (int k = 0; k < KP; k += 2) {
@@ -178,24 +287,26 @@ __global__ void __launch_bounds__(kEmThreads, 1)
 #pragma unroll
             for (int k = 0; k < K; ++k) v[k] = 0.0;
             double dsum = 0.0;
-            double tprev = 0.0;
-#pragma unroll
+            const double *ta_p = row;  // walked separately so that `a` only ever indexes the constant bank
+            double *tt_p = crow;
+#pragma unroll 1
             for (int a = 0; a < K; ++a) {
-                const double ta = row[a];
+                const double ta = *ta_p++;
+                const int pa = pbase + a * (K * KP);
                 double u = 0.0;
 #pragma unroll
                 for (int b = 0; b < K; ++b) {
-                    const double2 *pp = reinterpret_cast<const double2 *>(spr + (a * K + b) * KP);
                     const double ab = ta * tb[b];
                     double q0 = 0.0, q1 = 0.0;
 #pragma unroll
-                    for (int c2 = 0; c2 < KP / 2; ++c2) {
-                        const double2 pv = pp[c2];
-                        q0 = fma(pv.x, tc[2 * c2], q0);
-                        w[2 * c2] = fma(ab, pv.x, w[2 * c2]);
-                        if (2 * c2 + 1 < K) {
-                            q1 = fma(pv.y, tc[2 * c2 + 1], q1);
-                            w[2 * c2 + 1] = fma(ab, pv.y, w[2 * c2 + 1]);
+                    for (int c = 0; c < K; c += 2) {
+                        const double p0 = c_pem[pa + b * KP + c];
+                        q0 = fma(p0, tc[c], q0);
+                        w[c] = fma(ab, p0, w[c]);
+                        if (c + 1 < K) {
+                            const double p1 = c_pem[pa + b * KP + c + 1];
+                            q1 = fma(p1, tc[c + 1], q1);
+                            w[c + 1] = fma(ab, p1, w[c + 1]);
                         }
                     }
                     const double q = q0 + q1;
@@ -204,22 +315,19 @@ __global__ void __launch_bounds__(kEmThreads, 1)
                 }
                 const double tt = ta * u;
                 dsum += tt;
-                if (a & 1) {
-                    *reinterpret_cast<double2 *>(crow + a - 1) = make_double2(tprev, tt);
-                } else if (a == K - 1) {
-                    crow[a] = tt;
-                }
-                tprev = tt;
+                if constexpr (C::kPrivateS) *tt_p++ = tt;  // slot-a contribution (K >= 5: from M_g in em_finalize_kernel)
             }
             const double d = TIP_EPS + dsum;
             const double s = cnt / d;
-            ll += cnt * log(d);
-            // contributions: slot a (scale what is already there), slot b, slot c; s*th_c into the stage
+            if constexpr (LL) ll += cnt * log(d);  // by-product, only on request (TIP_EM_WITH_LOGLIK)
+            // contributions of slot b and slot c; s*th_c into the stage for phase B
 #pragma unroll
             for (int k = 0; k < KP; k += 2) {
-                double2 ca = *reinterpret_cast<double2 *>(crow + k);
-                ca.x *= s; ca.y *= s;
-                *reinterpret_cast<double2 *>(crow + k) = ca;
+                if constexpr (C::kPrivateS) {
+                    double2 ca = *reinterpret_cast<double2 *>(crow + k);
+                    ca.x *= s; ca.y *= s;
+                    *reinterpret_cast<double2 *>(crow + k) = ca;
+                }
                 const double vb1 = (k + 1 < K) ? v[k + 1] : 0.0;
                 *reinterpret_cast<double2 *>(crow + KP + k) = make_double2(s * tb[k] * v[k], s * tb[k + 1] * vb1);
                 const double sc0 = s * tc[k], sc1 = s * tc[k + 1];
@@ -243,118 +351,284 @@ __global__ void __launch_bounds__(kEmThreads, 1)
         __syncwarp();
 
         // ================= scatter theta statistics =================
-        {
+        if (!(dbg & 1)) {
             const int *idw = reinterpret_cast<const int *>(ids);
-            // slot a: run-length pre-reduction.  lane -> (k = lane % K, part = lane / K); each part
-            // walks a contiguous range of the 32 links and emits one reduction per run of equal gene.
-            constexpr int NPART = 32 / K > 4 ? 4 : (32 / K);  // K<=8 -> 4 parts, 9,10 -> 3 parts
-            constexpr int LPP = (32 + NPART - 1) / NPART;
-            const int k = lane % K, part = lane / K;
-            if (part < NPART) {
-                const int l0 = part * LPP;
-                const int l1 = (l0 + LPP < 32) ? l0 + LPP : 32;
-                double acc = 0.0;
-                int g = idw[l0 * 4];
-                for (int l = l0; l < l1; ++l) {
-                    const int gl = idw[l * 4];
-                    if (gl != g) {
-                        if (acc != 0.0) red_add_f64(stats + (int64_t)g * K + k, acc);
-                        acc = 0.0;
-                        g = gl;
+            if constexpr (C::kPrivateS) {
+                // slot a: run-length pre-reduction.  lane -> (k = lane % K, part = lane / K); each part
+                // walks a contiguous range of the 32 links and emits one reduction per run of equal gene.
+                constexpr int NPART = 32 / K > 4 ? 4 : (32 / K);
+                constexpr int LPP = (32 + NPART - 1) / NPART;
+                const int k = lane % K, part = lane / K;
+                if (part < NPART) {
+                    const int l0 = part * LPP;
+                    const int l1 = (l0 + LPP < 32) ? l0 + LPP : 32;
+                    double acc = 0.0;
+                    int g = idw[l0 * 4];
+                    for (int l = l0; l < l1; ++l) {
+                        const int gl = idw[l * 4];
+                        if (gl != g) {
+                            red_add_f64_nz(stats + (int64_t)g * K + k, acc);
+                            acc = 0.0;
+                            g = gl;
+                        }
+                        acc += cbuf[l * RS + k];
                     }
-                    acc += cbuf[l * RS + k];
+                    red_add_f64_nz(stats + (int64_t)g * K + k, acc);
                 }
-                if (acc != 0.0) red_add_f64(stats + (int64_t)g * K + k, acc);
             }
-            // slots b, c: row-contiguous reductions
-#pragma unroll 4
-            for (int i = 0; i < 2 * K; ++i) {
-                const int idx = i * 32 + lane;
-                const int l = idx / (2 * K), rem = idx - l * (2 * K);
-                const int slot = 1 + rem / K, kk = rem % K;
-                const double val = cbuf[l * RS + slot * KP + kk];
-                if (val != 0.0) red_add_f64(stats + (int64_t)idw[l * 4 + slot] * K + kk, val);
+            // slots b, c
+            if constexpr (K % 2 == 0) {
+                // one bulk add-reduction per (link, slot): the 8K-byte row goes to the TMA unit
+                fence_async_smem();
+                if (cnt != 0.0) {
+                    const double *crow = cbuf + lane * RS;
+                    bulk_red_add_f64(stats + (int64_t)me.y * K, crow + KP, K * 8);
+                    bulk_red_add_f64(stats + (int64_t)me.z * K, crow + 2 * KP, K * 8);
+                }
+                bulk_commit();
+            } else {
+                using SM = ScatterMap<K>;
+                const double *cb = cbuf;
+                const int *ib = idw;
+#pragma unroll 1
+                for (int per = 0; per < SM::NPERIOD; ++per) {
+#pragma unroll
+                    for (int ph = 0; ph < SM::PER; ++ph) {
+                        const unsigned pk = sc_pack[ph];
+                        const double val = cb[pk & 0xffffu];
+                        const int g = ib[(pk >> 16) & 0xffu];
+                        red_add_f64_nz(stats + (int64_t)g * K + (pk >> 24), val);
+                    }
+                    cb += SM::LPP * RS;
+                    ib += SM::LPP * 4;
+                }
             }
         }
 
-        // ================= phase B: lanes = cells of S =================
-        if constexpr (!C::kPrivateS) {
+        // ====== phase B: M_g[b][c] += th_b[b] * (s th_c[c]), flushed per run of equal slot-a gene ======
+        if constexpr (!C::kPrivateS) if (!(dbg & 2)) {
+            const int *idw = reinterpret_cast<const int *>(ids);
+            double M[CB];
+#pragma unroll
+            for (int j = 0; j < CB; ++j) M[j] = 0.0;
+            double *Mr = Mg + (int64_t)r_v * P * (K * K) + b_lane * K + c0;  // this lane's cells of M_g, gene 0
+            auto flush_M = [&](int g) {
+                double *dst = Mr + (int64_t)g * (K * K);
+#pragma unroll
+                for (int j = 0; j < CB; ++j) {
+                    if (b_active && c0 + j < K) red_add_f64_nz(dst + j, M[j]);
+                    M[j] = 0.0;
+                }
+            };
+            int a_prev = idw[0];
 #pragma unroll 4
             for (int l = 0; l < 32; ++l) {
                 const double *rw = stage + l * RS;
-                const double ta = rw[al_b];
-                double tbv[BG];
-                if constexpr (BG % 2 == 0) {
+                const int a_l = idw[l * 4];  // same address for every lane: the branch is warp-uniform
+                if (a_l != a_prev) {
+                    flush_M(a_prev);
+                    a_prev = a_l;
+                }
+                const double tb = rw[KP + b_lane];
+                double sc[CB];
+                if constexpr (CB % 2 == 0) {
 #pragma unroll
-                    for (int j = 0; j < BG; j += 2) {
-                        const double2 t2 = *reinterpret_cast<const double2 *>(rw + KP + be0 + j);
-                        tbv[j] = t2.x; tbv[j + 1] = t2.y;
+                    for (int j = 0; j < CB; j += 2) {
+                        const double2 t2 = *reinterpret_cast<const double2 *>(rw + 2 * KP + c0 + j);
+                        sc[j] = t2.x; sc[j + 1] = t2.y;
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < BG; ++j) tbv[j] = rw[KP + be0 + j];
-                }
-                double sc[KP];
-#pragma unroll
-                for (int c = 0; c < KP; c += 2) {
-                    const double2 t2 = *reinterpret_cast<const double2 *>(rw + 2 * KP + c);
-                    sc[c] = t2.x; sc[c + 1] = t2.y;
+                    for (int j = 0; j < CB; ++j) sc[j] = rw[2 * KP + c0 + j];
                 }
 #pragma unroll
-                for (int j = 0; j < BG; ++j) {
-                    const double ab = ta * tbv[j];
-#pragma unroll
-                    for (int c = 0; c < K; ++c) Sacc[j * K + c] = fma(ab, sc[c], Sacc[j * K + c]);
-                }
+                for (int j = 0; j < CB; ++j) M[j] = fma(tb, sc[j], M[j]);
             }
+            flush_M(a_prev);
         }
         __syncwarp();
+        if (NBUF == 2) buf ^= 1;
     }
-    flush_S(cur_r);
-    ll = warp_sum(ll);
-    if (lane == 0 && ll != 0.0) red_add_f64(stats + stats_off_ll(P, K), ll);
-    __syncthreads();
-    double *Sg = stats + stats_off_S(P, K);
-    for (int e = threadIdx.x; e < 2 * K3; e += kEmThreads) {
-        const double v = Ssm[e];
-        if (v != 0.0) red_add_f64(Sg + e, v);
+    if constexpr (C::kPrivateS) flush_S(cur_r);
+    if constexpr (LL) {
+        ll = warp_sum(ll);
+        if (lane == 0 && ll != 0.0) red_add_f64(stats + stats_off_ll(P, K), ll);
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-gene finish of the gene-segmented factorisation (K >= 5), once per iteration:
+//   Ntheta[g][a] += th_g[a] * sum_r sum_bc p[a][b][c][r] M_{r,g}[b][c]
+//   S[r][a][b][c] += sum_g th_g[a] * M_{r,g}[b][c]
+// One CTA per chunk of genes; thread = cell (a, b, c) for S, thread = (gene, a) for Ntheta.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFinThreads = 256;
+constexpr int kFinGenes = 8;  // genes staged per pass
+
 template <int K>
-static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, const double *theta, const double *p,
-                           double *stats, cudaStream_t st)
+__global__ void __launch_bounds__(kFinThreads)
+    em_finalize_kernel(int P, const double *__restrict__ theta, const double *__restrict__ p,
+                       const double *__restrict__ Mg, double *__restrict__ stats)
 {
-    using C = EmCfg<K>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        attr_done = true;
+    constexpr int KK = K * K, K3 = K * K * K;
+    constexpr int CPT = (K3 + kFinThreads - 1) / kFinThreads;  // S cells per thread
+    __shared__ double sM[kFinGenes][KK];
+    __shared__ double sT[kFinGenes][K];
+    const int tid = threadIdx.x;
+    const int per = (P + gridDim.x - 1) / gridDim.x;
+    const int g_lo = blockIdx.x * per, g_hi = (g_lo + per < P) ? g_lo + per : P;
+    for (int r = 0; r < 2; ++r) {
+        double acc[CPT];
+        int ca[CPT], cbc[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            int cell = tid + i * kFinThreads;
+            if (cell >= K3) cell = K3 - 1;
+            ca[i] = cell / KK;
+            cbc[i] = cell - ca[i] * KK;
+            acc[i] = 0.0;
+        }
+        for (int g0 = g_lo; g0 < g_hi; g0 += kFinGenes) {
+            const int ng = (g_hi - g0 < kFinGenes) ? g_hi - g0 : kFinGenes;
+            __syncthreads();
+            for (int e = tid; e < ng * KK; e += kFinThreads) sM[e / KK][e % KK] = Mg[((int64_t)r * P + g0) * KK + e];
+            for (int e = tid; e < ng * K; e += kFinThreads) sT[e / K][e % K] = theta[(int64_t)g0 * K + e];
+            __syncthreads();
+            for (int gi = 0; gi < ng; ++gi) {
+#pragma unroll
+                for (int i = 0; i < CPT; ++i) acc[i] = fma(sT[gi][ca[i]], sM[gi][cbc[i]], acc[i]);
+            }
+            if (tid < ng * K) {
+                // slot-a statistic; this thread owns (gene, a) for both ratings, and nothing else touches the
+                // theta statistics while this kernel runs, so a plain read-modify-write is enough
+                const int gi = tid / K, a = tid - gi * K;
+                const double *pa = p + (int64_t)a * KK * 2 + r;
+                double t = 0.0;
+                for (int bc = 0; bc < KK; ++bc) t = fma(__ldg(pa + 2 * bc), sM[gi][bc], t);
+                const double contrib = sT[gi][a] * t;
+                if (contrib != 0.0) stats[(int64_t)(g0 + gi) * K + a] += contrib;
+            }
+        }
+        double *S = stats + stats_off_S(P, K) + (int64_t)r * K3;
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+            const int cell = tid + i * kFinThreads;
+            if (cell < K3 && acc[i] != 0.0) red_add_f64(S + cell, acc[i]);
+        }
+    }
+}
+
+static int g_slot_counter = 0;
+
+// TIP_EM_VARIANT (environment, read once) selects resident warps per SM / gather buffering for tuning runs:
+//   0 (default) = 12 warp-CTAs per SM (<=168 regs), single-buffered gather
+//   1 = 8 per SM (<=255 regs), double-buffered      2 = 12 per SM, double-buffered      3 = 16 per SM (<=128 regs)
+// All variants produce the same statistics.
+static int em_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TIP_EM_VARIANT");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 3) v = 0;
+    }
+    return v;
+}
+
+// TIP_EM_DEBUG (environment): bit 0 skips the theta scatter, bit 1 skips phase B - timing experiments only
+static int em_debug()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TIP_EM_DEBUG");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+template <int K, int NBUF, int MINB, bool LL>
+static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, int slot,
+                          double *stats, double *Mg, cudaStream_t st)
+{
+    using C = EmCfg<K, NBUF>;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)C::SMEM));
+        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL>,
+                                            cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int nb = 0;
+        TIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, em_fused_kernel<K, NBUF, MINB, LL>, 32, C::SMEM));
+        TIP_REQUIRE(nb >= 1, "em_fused_kernel<%d> does not fit on an SM (smem %zu)", K, C::SMEM);
+        blocks_per_sm = nb;
     }
     const int64_t n_tiles = n_rows / 32;
-    int64_t want = (n_tiles + kEmWarps - 1) / kEmWarps;
-    int grid = (int)(want < sm_count() ? want : sm_count());
+    TIP_REQUIRE(n_tiles < (1ll << 31), "tip_em_step: more than 2^31 tiles in one shard");
+    int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+    int grid = (int)(n_tiles < cap ? n_tiles : cap);
     if (grid < 1) grid = 1;
-    em_fused_kernel<K><<<grid, kEmThreads, C::SMEM, st>>>(P, rows, n_tiles, theta, p, stats);
+    em_fused_kernel<K, NBUF, MINB, LL><<<grid, 32, C::SMEM, st>>>(P, rows, (int)n_tiles, (int)(n_rows_r0 / 32), theta, slot,
+                                                                 stats, Mg, em_debug());
     TIP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, const double *theta, const double *p,
-                    double *stats, cudaStream_t st, bool *handled)
+size_t em_tuned_workspace_bytes(int P, int K)
+{
+    if (K <= 4 || K > 10) return 0;
+    return sizeof(double) * 2 * (size_t)P * K * K;  // M_g[r][gene][b][c]
+}
+
+template <int K>
+static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
+                           const double *p, double *stats, double *ws, bool with_ll, cudaStream_t st)
+{
+    constexpr int KP = K + (K & 1);
+    static double *stage_ptr = nullptr;
+    if (!stage_ptr) TIP_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&stage_ptr), g_pstage));
+    const int slot = (g_slot_counter++) % kPSlots;
+    const int n = 2 * K * K * KP;
+    stage_p_kernel<<<(n + 255) / 256, 256, 0, st>>>(K, KP, p, stage_ptr + slot * kPSlotDoubles);
+    TIP_CHECK_CUDA(cudaGetLastError());
+    TIP_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_pem, stage_ptr + slot * kPSlotDoubles, sizeof(double) * n,
+                                           sizeof(double) * slot * kPSlotDoubles, cudaMemcpyDeviceToDevice, st));
+    if (K > 4) TIP_CHECK_CUDA(cudaMemsetAsync(ws, 0, em_tuned_workspace_bytes(P, K), st));
+    int rc;
+    if (with_ll) {
+        rc = launch_variant<K, 1, 12, true>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st);
+    } else {
+        switch (em_variant()) {
+            case 1: rc = launch_variant<K, 2, 8, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
+            case 2: rc = launch_variant<K, 2, 12, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
+            case 3: rc = launch_variant<K, 1, 16, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
+            default: rc = launch_variant<K, 1, 12, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
+        }
+    }
+    if (rc != 0) return rc;
+    if constexpr (K > 4) {
+        int grid = sm_count() * 2;
+        if (grid > P) grid = P;
+        em_finalize_kernel<K><<<grid, kFinThreads, 0, st>>>(P, theta, p, ws, stats);
+        TIP_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
+                    const double *p, double *stats, double *ws, bool with_ll, cudaStream_t st, bool *handled)
 {
     *handled = true;
     switch (K) {
-        case 1: return launch_em_fused<1>(P, rows, n_rows, theta, p, stats, st);
-        case 2: return launch_em_fused<2>(P, rows, n_rows, theta, p, stats, st);
-        case 3: return launch_em_fused<3>(P, rows, n_rows, theta, p, stats, st);
-        case 4: return launch_em_fused<4>(P, rows, n_rows, theta, p, stats, st);
-        case 5: return launch_em_fused<5>(P, rows, n_rows, theta, p, stats, st);
-        case 6: return launch_em_fused<6>(P, rows, n_rows, theta, p, stats, st);
-        case 7: return launch_em_fused<7>(P, rows, n_rows, theta, p, stats, st);
-        case 8: return launch_em_fused<8>(P, rows, n_rows, theta, p, stats, st);
-        case 9: return launch_em_fused<9>(P, rows, n_rows, theta, p, stats, st);
-        case 10: return launch_em_fused<10>(P, rows, n_rows, theta, p, stats, st);
+        case 1: return launch_em_fused<1>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
+        case 2: return launch_em_fused<2>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
+        case 3: return launch_em_fused<3>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
+        case 4: return launch_em_fused<4>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
+        case 5: return launch_em_fused<5>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
+        case 6: return launch_em_fused<6>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
+        case 7: return launch_em_fused<7>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
+        case 8: return launch_em_fused<8>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
+        case 9: return launch_em_fused<9>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
+        case 10: return launch_em_fused<10>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
         default: *handled = false; return 0;
     }
 }
