@@ -300,13 +300,13 @@ __global__ void __launch_bounds__(32, MINB)
                     double q0 = 0.0, q1 = 0.0;
 #pragma unroll
                     for (int c = 0; c < K; c += 2) {
-                        const double p0 = c_pem[pa + b * KP + c];
-                        q0 = fma(p0, tc[c], q0);
-                        w[c] = fma(ab, p0, w[c]);
+                        // (pa + b*KP + c) is even: one 16-byte uniform load feeds four DFMA
+                        const double2 pv = *reinterpret_cast<const double2 *>(&c_pem[pa + b * KP + c]);
+                        q0 = fma(pv.x, tc[c], q0);
+                        w[c] = fma(ab, pv.x, w[c]);
                         if (c + 1 < K) {
-                            const double p1 = c_pem[pa + b * KP + c + 1];
-                            q1 = fma(p1, tc[c + 1], q1);
-                            w[c + 1] = fma(ab, p1, w[c + 1]);
+                            q1 = fma(pv.y, tc[c + 1], q1);
+                            w[c + 1] = fma(ab, pv.y, w[c + 1]);
                         }
                     }
                     const double q = q0 + q1;
@@ -463,7 +463,8 @@ __global__ void __launch_bounds__(32, MINB)
 // One CTA per chunk of genes; thread = cell (a, b, c) for S, thread = (gene, a) for Ntheta.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFinThreads = 256;
-constexpr int kFinGenes = 8;  // genes staged per pass
+constexpr int kFinWarps = kFinThreads / 32;
+constexpr int kFinChunk = 48;  // genes staged in shared memory per pass (both ratings)
 
 template <int K>
 __global__ void __launch_bounds__(kFinThreads)
@@ -472,50 +473,84 @@ __global__ void __launch_bounds__(kFinThreads)
 {
     constexpr int KK = K * K, K3 = K * K * K;
     constexpr int CPT = (K3 + kFinThreads - 1) / kFinThreads;  // S cells per thread
-    __shared__ double sM[kFinGenes][KK];
-    __shared__ double sT[kFinGenes][K];
-    const int tid = threadIdx.x;
+    constexpr int BPL = (KK + 31) / 32;                        // (b,c) pairs per lane
+    extern __shared__ __align__(16) double fsm[];
+    double *sP = fsm;                         // [2][K3]   p[r][a][bc]
+    double *sT = sP + 2 * K3;                 // [kFinChunk][K]
+    double *sM = sT + kFinChunk * K;          // [2][kFinChunk][KK]
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
     const int per = (P + gridDim.x - 1) / gridDim.x;
     const int g_lo = blockIdx.x * per, g_hi = (g_lo + per < P) ? g_lo + per : P;
-    for (int r = 0; r < 2; ++r) {
-        double acc[CPT];
-        int ca[CPT], cbc[CPT];
+    for (int e = tid; e < 2 * K3; e += kFinThreads) sP[(e & 1) * K3 + (e >> 1)] = p[e];
+    int ca[CPT], cbc[CPT];
+    double acc0[CPT], acc1[CPT];
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-            int cell = tid + i * kFinThreads;
-            if (cell >= K3) cell = K3 - 1;
-            ca[i] = cell / KK;
-            cbc[i] = cell - ca[i] * KK;
-            acc[i] = 0.0;
+    for (int i = 0; i < CPT; ++i) {
+        int cell = tid + i * kFinThreads;
+        if (cell >= K3) cell = K3 - 1;
+        ca[i] = cell / KK;
+        cbc[i] = cell - ca[i] * KK;
+        acc0[i] = acc1[i] = 0.0;
+    }
+    for (int g0 = g_lo; g0 < g_hi; g0 += kFinChunk) {
+        const int ng = (g_hi - g0 < kFinChunk) ? g_hi - g0 : kFinChunk;
+        __syncthreads();
+        // stage this chunk: all loads independent, so one memory round trip covers the lot
+        const int nM = ng * KK;
+#pragma unroll 8
+        for (int e = tid; e < nM; e += kFinThreads) {
+            sM[e] = __ldg(Mg + (int64_t)g0 * KK + e);
+            sM[kFinChunk * KK + e] = __ldg(Mg + ((int64_t)P + g0) * KK + e);
         }
-        for (int g0 = g_lo; g0 < g_hi; g0 += kFinGenes) {
-            const int ng = (g_hi - g0 < kFinGenes) ? g_hi - g0 : kFinGenes;
-            __syncthreads();
-            for (int e = tid; e < ng * KK; e += kFinThreads) sM[e / KK][e % KK] = Mg[((int64_t)r * P + g0) * KK + e];
-            for (int e = tid; e < ng * K; e += kFinThreads) sT[e / K][e % K] = theta[(int64_t)g0 * K + e];
-            __syncthreads();
-            for (int gi = 0; gi < ng; ++gi) {
+        for (int e = tid; e < ng * K; e += kFinThreads) sT[e] = __ldg(theta + (int64_t)g0 * K + e);
+        __syncthreads();
+        // p statistic: thread = cells of S
+        for (int gi = 0; gi < ng; ++gi) {
 #pragma unroll
-                for (int i = 0; i < CPT; ++i) acc[i] = fma(sT[gi][ca[i]], sM[gi][cbc[i]], acc[i]);
-            }
-            if (tid < ng * K) {
-                // slot-a statistic; this thread owns (gene, a) for both ratings, and nothing else touches the
-                // theta statistics while this kernel runs, so a plain read-modify-write is enough
-                const int gi = tid / K, a = tid - gi * K;
-                const double *pa = p + (int64_t)a * KK * 2 + r;
-                double t = 0.0;
-                for (int bc = 0; bc < KK; ++bc) t = fma(__ldg(pa + 2 * bc), sM[gi][bc], t);
-                const double contrib = sT[gi][a] * t;
-                if (contrib != 0.0) stats[(int64_t)(g0 + gi) * K + a] += contrib;
+            for (int i = 0; i < CPT; ++i) {
+                const double th = sT[gi * K + ca[i]];
+                acc0[i] = fma(th, sM[gi * KK + cbc[i]], acc0[i]);
+                acc1[i] = fma(th, sM[(kFinChunk + gi) * KK + cbc[i]], acc1[i]);
             }
         }
-        double *S = stats + stats_off_S(P, K) + (int64_t)r * K3;
+        // slot-a statistic: warp = gene, lanes split the (b,c) pairs, K interleaved butterfly reductions
+        for (int gi = warp; gi < ng; gi += kFinWarps) {
+            double t[K];
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-            const int cell = tid + i * kFinThreads;
-            if (cell < K3 && acc[i] != 0.0) red_add_f64(S + cell, acc[i]);
+            for (int a = 0; a < K; ++a) t[a] = 0.0;
+#pragma unroll
+            for (int i = 0; i < BPL; ++i) {
+                const int bc = lane + 32 * i;
+                if (bc < KK) {
+                    const double m0 = sM[gi * KK + bc], m1 = sM[(kFinChunk + gi) * KK + bc];
+#pragma unroll
+                    for (int a = 0; a < K; ++a) t[a] = fma(sP[K3 + a * KK + bc], m1, fma(sP[a * KK + bc], m0, t[a]));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int a = 0; a < K; ++a) t[a] += __shfl_xor_sync(0xffffffffu, t[a], o);
+#pragma unroll
+            for (int a = 0; a < K; ++a)
+                if (lane == a) red_add_f64_nz(stats + (int64_t)(g0 + gi) * K + a, sT[gi * K + a] * t[a]);
         }
     }
+    double *S = stats + stats_off_S(P, K);
+#pragma unroll
+    for (int i = 0; i < CPT; ++i) {
+        const int cell = tid + i * kFinThreads;
+        if (cell < K3) {
+            red_add_f64_nz(S + cell, acc0[i]);
+            red_add_f64_nz(S + K3 + cell, acc1[i]);
+        }
+    }
+}
+
+template <int K>
+constexpr size_t fin_smem_bytes()
+{
+    return sizeof(double) * (2 * K * K * K + kFinChunk * K + 2 * kFinChunk * K * K);
 }
 
 static int g_slot_counter = 0;
@@ -606,9 +641,15 @@ static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_ro
     }
     if (rc != 0) return rc;
     if constexpr (K > 4) {
-        int grid = sm_count() * 2;
+        static bool fin_attr = false;
+        if (!fin_attr) {
+            TIP_CHECK_CUDA(cudaFuncSetAttribute(em_finalize_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)fin_smem_bytes<K>()));
+            fin_attr = true;
+        }
+        int grid = sm_count();
         if (grid > P) grid = P;
-        em_finalize_kernel<K><<<grid, kFinThreads, 0, st>>>(P, theta, p, ws, stats);
+        em_finalize_kernel<K><<<grid, kFinThreads, fin_smem_bytes<K>(), st>>>(P, theta, p, ws, stats);
         TIP_CHECK_CUDA(cudaGetLastError());
     }
     return 0;
