@@ -89,10 +89,11 @@ int tip_normalise(int P, int K, const double *d_stats, const int32_t *d_deg, dou
 
 /* ---- Model.compute_likelihood (TIP.py:952-974) ----
  * *d_out = sum_rows count * log(eps + sum_abc th th th p_r).  Deterministic summation order.
+ * Rows as packed by tip_pack_rows (n_rows_r0 = h_part[0]); flags: TIP_EM_FORCE_GENERIC selects the any-K kernel.
  * d_ws: tip_loglik_workspace_bytes() bytes of scratch. */
 size_t tip_loglik_workspace_bytes(void);
-int tip_loglik(int P, int K, const void *d_rows, int64_t n_rows, const double *d_theta, const double *d_p,
-               double *d_out, void *d_ws, void *stream);
+int tip_loglik(int P, int K, const void *d_rows, int64_t n_rows, int64_t n_rows_r0, const double *d_theta,
+               const double *d_p, double *d_out, void *d_ws, unsigned flags, void *stream);
 
 /* ---- Model.do_prediction over a whole test set (TIP.py:530-547, 564-565) ----
  * d_scores[t] = sum_abc th[g1[t]][a] th[g2[t]][b] th[g3[t]][c] p[a][b][c][1]   (no eps). */

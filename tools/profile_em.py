@@ -38,4 +38,10 @@ ts_s = sorted(ts[1:]) if len(ts) > 1 else ts
 med = ts_s[len(ts_s) // 2]
 print("em_step over %d iters: min %.3f ms  median %.3f ms  (%.3e link-updates/s at median)" % (
     len(ts_s), ts_s[0], med, L / med * 1e3))
-print("loglik", eng.loglik("train"))
+ll = eng.loglik("train")
+a.record()
+for _ in range(5):
+    ll = eng.loglik("train")
+b.record()
+torch.cuda.synchronize()
+print("loglik %.6f   %.3f ms per call (incl. readback)" % (ll, a.elapsed_time(b) / 5))

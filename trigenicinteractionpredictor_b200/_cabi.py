@@ -35,7 +35,8 @@ SIGNATURES = {
                             c_uint, c_void_p]),
     "tip_normalise": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tip_loglik_workspace_bytes": (c_size_t, []),
-    "tip_loglik": (c_int, [c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tip_loglik": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_uint,
+                           c_void_p]),
     "tip_score": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tip_metrics_workspace_bytes": (c_int, [c_int64, _psz]),
     "tip_metrics": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -73,16 +73,19 @@ extern "C" int tip_normalise(int P, int K, const double *d_stats, const int32_t 
 
 extern "C" size_t tip_loglik_workspace_bytes(void) { return loglik_ws_bytes(); }
 
-extern "C" int tip_loglik(int P, int K, const void *d_rows, int64_t n_rows, const double *d_theta, const double *d_p,
-                          double *d_out, void *d_ws, void *stream)
+extern "C" int tip_loglik(int P, int K, const void *d_rows, int64_t n_rows, int64_t n_rows_r0, const double *d_theta,
+                          const double *d_p, double *d_out, void *d_ws, unsigned flags, void *stream)
 {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    TIP_REQUIRE(P > 0 && valid_K(K) && d_theta && d_p && d_out && d_ws && n_rows >= 0, "tip_loglik: bad arguments");
+    TIP_REQUIRE(P > 0 && valid_K(K) && d_theta && d_p && d_out && d_ws && n_rows >= 0 && n_rows % 32 == 0 &&
+                    n_rows_r0 >= 0 && n_rows_r0 <= n_rows && n_rows_r0 % 32 == 0,
+                "tip_loglik: bad arguments");
     if (n_rows == 0) {
         TIP_CHECK_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), st));
         return 0;
     }
-    return launch_loglik(K, reinterpret_cast<const int4 *>(d_rows), n_rows, d_theta, d_p, d_out, d_ws, st);
+    return launch_loglik(K, reinterpret_cast<const int4 *>(d_rows), n_rows, n_rows_r0, d_theta, d_p, d_out, d_ws,
+                         (flags & TIP_EM_FORCE_GENERIC) != 0, st);
 }
 
 extern "C" int tip_score(int P, int K, const int32_t *d_g1, const int32_t *d_g2, const int32_t *d_g3, int64_t T,

@@ -614,11 +614,10 @@ size_t em_tuned_workspace_bytes(int P, int K)
     return sizeof(double) * 2 * (size_t)P * K * K;  // M_g[r][gene][b][c]
 }
 
-template <int K>
-static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
-                           const double *p, double *stats, double *ws, bool with_ll, cudaStream_t st)
+// p -> E-step layout -> constant bank slot (stream-ordered); returns the slot in *slot_out
+static int upload_p_const(int K, const double *p, cudaStream_t st, int *slot_out)
 {
-    constexpr int KP = K + (K & 1);
+    const int KP = K + (K & 1);
     static double *stage_ptr = nullptr;
     if (!stage_ptr) TIP_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&stage_ptr), g_pstage));
     const int slot = (g_slot_counter++) % kPSlots;
@@ -627,6 +626,19 @@ static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_ro
     TIP_CHECK_CUDA(cudaGetLastError());
     TIP_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_pem, stage_ptr + slot * kPSlotDoubles, sizeof(double) * n,
                                            sizeof(double) * slot * kPSlotDoubles, cudaMemcpyDeviceToDevice, st));
+    *slot_out = slot;
+    return 0;
+}
+
+template <int K>
+static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
+                           const double *p, double *stats, double *ws, bool with_ll, cudaStream_t st)
+{
+    int slot = 0;
+    {
+        const int rc0 = upload_p_const(K, p, st, &slot);
+        if (rc0 != 0) return rc0;
+    }
     if (K > 4) TIP_CHECK_CUDA(cudaMemsetAsync(ws, 0, em_tuned_workspace_bytes(P, K), st));
     int rc;
     if (with_ll) {
@@ -653,6 +665,135 @@ static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_ro
         TIP_CHECK_CUDA(cudaGetLastError());
     }
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Model.compute_likelihood on the same machinery (K <= 10): lane = link, only the normaliser
+//   d = eps + sum_a th_a[a] sum_b th_b[b] sum_c p[abc] th_c[c]        (K^3 + K^2 DFMA per link)
+// Per-CTA partial sums land in `partials`; the last CTA to finish adds them in index order, so the
+// result does not depend on scheduling.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(32, 16)
+    loglik_fused_kernel(const int4 *__restrict__ rows, int n_tiles, int n_tiles_r0, const double *__restrict__ theta,
+                        int p_slot, double *__restrict__ partials, unsigned *__restrict__ counter, double *__restrict__ out)
+{
+    using C = EmCfg<K, 1>;
+    constexpr int KP = C::KP, RS = C::RS;
+    __shared__ __align__(16) double stage[32 * RS];
+    __shared__ __align__(16) int4 ids_sm[32];
+    const int lane = threadIdx.x;
+    unsigned bx_v, gx_v;  // per-lane copies of the block coordinates, see em_fused_kernel
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(bx_v));
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(gx_v));
+    const int4 *rp = rows + (int64_t)bx_v * 32 + lane;
+    const int64_t rstride = (int64_t)gx_v * 32;
+    double ll = 0.0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        __syncwarp();
+        ids_sm[lane] = *rp;
+        rp += rstride;
+        __syncwarp();
+        gather_tile<K, RS, KP>(theta, ids_sm, stage, lane);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        const double cnt = (double)row_count(ids_sm[lane].w);
+        const int r = t >= n_tiles_r0 ? 1 : 0;
+        const int pbase = p_slot * kPSlotDoubles + r * (K * K * KP);
+        const double *row = stage + lane * RS;
+        double tb[KP], tc[KP];
+#pragma unroll
+        for (int k = 0; k < KP; k += 2) {
+            const double2 b2 = *reinterpret_cast<const double2 *>(row + KP + k);
+            const double2 c2 = *reinterpret_cast<const double2 *>(row + 2 * KP + k);
+            tb[k] = b2.x; tb[k + 1] = b2.y;
+            tc[k] = c2.x; tc[k + 1] = c2.y;
+        }
+        double dsum = 0.0;
+        const double *ta_p = row;
+#pragma unroll 1
+        for (int a = 0; a < K; ++a) {
+            const double ta = *ta_p++;
+            const int pa = pbase + a * (K * KP);
+            double u = 0.0;
+#pragma unroll
+            for (int b = 0; b < K; ++b) {
+                double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+                for (int c = 0; c < K; c += 2) {
+                    q0 = fma(c_pem[pa + b * KP + c], tc[c], q0);
+                    if (c + 1 < K) q1 = fma(c_pem[pa + b * KP + c + 1], tc[c + 1], q1);
+                }
+                u = fma(tb[b], q0 + q1, u);
+            }
+            dsum = fma(ta, u, dsum);
+        }
+        if (cnt != 0.0) ll += cnt * log(TIP_EPS + dsum);
+    }
+    ll = warp_sum(ll);
+    __shared__ bool last;
+    if (lane == 0) {
+        partials[bx_v] = ll;  // per-lane uses go through the clusterid copies (see em_fused_kernel)
+        __threadfence();
+        last = (atomicAdd(counter, 1u) == gx_v - 1);
+    }
+    __syncwarp();
+    if (last) {
+        __threadfence();
+        // fixed-order sum of the partials: lanes take strided slices, then a butterfly
+        double t = 0.0;
+        for (unsigned i = lane; i < gx_v; i += 32) t += reinterpret_cast<volatile double *>(partials)[i];
+        t = warp_sum(t);
+        if (lane == 0) {
+            *out = t;
+            *counter = 0;
+        }
+    }
+}
+
+template <int K>
+static int launch_loglik_fused(const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
+                               double *out, double *partials, unsigned *counter, int max_blocks, cudaStream_t st)
+{
+    int slot = 0;
+    {
+        const int rc0 = upload_p_const(K, p, st, &slot);
+        if (rc0 != 0) return rc0;
+    }
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        int nb = 0;
+        TIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, loglik_fused_kernel<K>, 32, 0));
+        blocks_per_sm = nb < 1 ? 1 : nb;
+    }
+    const int64_t n_tiles = n_rows / 32;
+    int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+    if (cap > max_blocks) cap = max_blocks;
+    int grid = (int)(n_tiles < cap ? n_tiles : cap);
+    if (grid < 1) grid = 1;
+    loglik_fused_kernel<K><<<grid, 32, 0, st>>>(rows, (int)n_tiles, (int)(n_rows_r0 / 32), theta, slot, partials, counter, out);
+    TIP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_loglik_tuned(int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
+                        double *out, double *partials, unsigned *counter, int max_blocks, cudaStream_t st, bool *handled)
+{
+    *handled = true;
+    switch (K) {
+        case 1: return launch_loglik_fused<1>(rows, n_rows, n_rows_r0, theta, p, out, partials, counter, max_blocks, st);
+        case 2: return launch_loglik_fused<2>(rows, n_rows, n_rows_r0, theta, p, out, partials, counter, max_blocks, st);
+        case 3: return launch_loglik_fused<3>(rows, n_rows, n_rows_r0, theta, p, out, partials, counter, max_blocks, st);
+        case 4: return launch_loglik_fused<4>(rows, n_rows, n_rows_r0, theta, p, out, partials, counter, max_blocks, st);
+        case 5: return launch_loglik_fused<5>(rows, n_rows, n_rows_r0, theta, p, out, partials, counter, max_blocks, st);
+        case 6: return launch_loglik_fused<6>(rows, n_rows, n_rows_r0, theta, p, out, partials, counter, max_blocks, st);
+        case 7: return launch_loglik_fused<7>(rows, n_rows, n_rows_r0, theta, p, out, partials, counter, max_blocks, st);
+        case 8: return launch_loglik_fused<8>(rows, n_rows, n_rows_r0, theta, p, out, partials, counter, max_blocks, st);
+        case 9: return launch_loglik_fused<9>(rows, n_rows, n_rows_r0, theta, p, out, partials, counter, max_blocks, st);
+        case 10: return launch_loglik_fused<10>(rows, n_rows, n_rows_r0, theta, p, out, partials, counter, max_blocks, st);
+        default: *handled = false; return 0;
+    }
 }
 
 int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,

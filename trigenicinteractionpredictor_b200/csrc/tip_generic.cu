@@ -180,7 +180,7 @@ int launch_em_generic(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_
 // ---------------------------------------------------------------------------------------------
 // log-likelihood: warp per row, per-CTA partials, last CTA sums them in index order
 // ---------------------------------------------------------------------------------------------
-constexpr int kLlMaxBlocks = 1024;
+constexpr int kLlMaxBlocks = 4096;
 
 __global__ void __launch_bounds__(kGenWarps *kWarp)
     gen_loglik_kernel(int K, const int4 *__restrict__ rows, int64_t n_rows, const double *__restrict__ theta,
@@ -246,11 +246,18 @@ __global__ void __launch_bounds__(kGenWarps *kWarp)
     }
 }
 
-int launch_loglik(int K, const int4 *rows, int64_t n_rows, const double *theta, const double *p, double *out,
-                  void *ws, cudaStream_t st)
+int launch_loglik(int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
+                  double *out, void *ws, bool force_generic, cudaStream_t st)
 {
     double *partials = reinterpret_cast<double *>(ws);
     unsigned *counter = reinterpret_cast<unsigned *>(partials + kLlMaxBlocks);
+    if (!force_generic && n_rows_r0 >= 0) {
+        TIP_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+        bool handled = false;
+        const int rc = launch_loglik_tuned(K, rows, n_rows, n_rows_r0, theta, p, out, partials, counter, kLlMaxBlocks, st,
+                                           &handled);
+        if (rc != 0 || handled) return rc;
+    }
     int64_t want = (n_rows + kGenWarps - 1) / kGenWarps;
     int grid = (int)((want < (int64_t)sm_count() * 4) ? want : (int64_t)sm_count() * 4);
     if (grid > kLlMaxBlocks) grid = kLlMaxBlocks;

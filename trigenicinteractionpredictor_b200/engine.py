@@ -173,9 +173,10 @@ class EMEngine:
         links = self.train if which == "train" else self.test
         if links is None:
             raise ValueError("no %s links set" % which)
-        _cabi.check(self.lib.tip_loglik(self.P, self.K, _ptr(links.rows), links.n_rows, _ptr(self.theta), _ptr(self.p),
-                                        _ptr(self.ll_out), _ptr(self.ll_ws), self._stream()), "tip_loglik")
-        self.launches += 1
+        _cabi.check(self.lib.tip_loglik(self.P, self.K, _ptr(links.rows), links.n_rows, links.n_rows_r0, _ptr(self.theta),
+                                        _ptr(self.p), _ptr(self.ll_out), _ptr(self.ll_ws), self.flags, self._stream()),
+                    "tip_loglik")
+        self.launches += 2 if (self.K <= 10 and not (self.flags & _cabi.TIP_EM_FORCE_GENERIC)) else 1
         if self.world > 1 and which == "train":
             _dist.allreduce_sum_(self.ll_out, self.group)
         return float(self.ll_out.item())
