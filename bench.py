@@ -322,7 +322,13 @@ def run_ours(args):
             line["cpu_baseline"] = None
         print(json.dumps(line))
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # ProcessGroupNCCL teardown (destroy_process_group / interpreter exit) was seen to hang on the
+        # GPU boxes after all work had completed; leave without running it
+        tdist.barrier(group)
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -1,0 +1,51 @@
+"""torchrun worker for tests/test_gpu_dist.py: link-sharded EM over NCCL vs the single-GPU iteration."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main(out_dir):
+    import torch
+    from trigenicinteractionpredictor_b200 import dist as tdist
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    rk, w, local = tdist.init_from_env(backend="nccl")
+    dev = torch.device("cuda", local)
+    rng = np.random.default_rng(3)
+    P, L, K = 500, 20000, 10
+    g = rng.integers(0, P, size=(L, 3)).astype(np.int32)
+    g[:P, 0] = np.arange(P)
+    lab = (rng.random(L) < 0.2).astype(np.int32)
+    theta = rng.dirichlet(np.ones(K), size=P)
+    pr = rng.random((K, K, K, 2))
+    pr /= pr.sum(axis=3, keepdims=True)
+    lo, hi = tdist.shard_bounds(L, rk, w)
+    eng = EMEngine(P, K, device=dev, group=torch.distributed.group.WORLD)
+    eng.set_train_links(g[lo:hi, 0], g[lo:hi, 1], g[lo:hi, 2], 1 - lab[lo:hi], lab[lo:hi])   # deg is allreduced inside
+    eng.set_params(theta, pr)
+    print(rk, "links set", flush=True)
+    eng.em_iterations(5, use_graph=True)
+    th, p = eng.get_params()
+    ll = eng.loglik("train")
+    print(rk, "sharded iterations done", ll, flush=True)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rk), th=th, p=p, ll=ll)
+    if rk == 0:
+        ref = EMEngine(P, K, device=dev)
+        ref.set_train_links(g[:, 0], g[:, 1], g[:, 2], 1 - lab, lab)
+        ref.set_params(theta, pr)
+        for _ in range(5):
+            ref.em_iteration()
+        th1, p1 = ref.get_params()
+        np.savez(os.path.join(out_dir, "single.npz"), th=th1, p=p1, ll=ref.loglik("train"))
+        print(rk, "single-GPU reference done", flush=True)
+    tdist.barrier()
+    torch.cuda.synchronize(dev)
+    sys.stdout.flush()
+    os._exit(0)      # skip ProcessGroupNCCL teardown, which was seen to hang on the GPU boxes
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

@@ -335,7 +335,10 @@ class Model:
             g1, g2, g3, n0, n1 = self._soa(self.links)
             deg = np.bincount(np.concatenate([g1, g2, g3]), minlength=self.P).astype(np.int32)
             self._deg_zero = bool((deg[: self.P] == 0).any())
-            world, rk = _dist.world_size(self._group), _dist.rank(self._group)
+            if self._group is not None:
+                world, rk = _dist.world_size(self._group), _dist.rank(self._group)
+            else:
+                world, rk = 1, 0
             lo, hi = _dist.shard_bounds(len(g1), rk, world)
             eng.set_train_links(g1[lo:hi], g2[lo:hi], g3[lo:hi], n0[lo:hi], n1[lo:hi], global_deg=deg)
             eng.set_test_links(*self._soa(self.test_links))

@@ -39,7 +39,8 @@ class EMEngine:
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.group = group
         self.flags = int(flags)
-        self.world = _dist.world_size(group)
+        # group=None means "this process alone" (NOT torch.distributed's default group): link shards are opt-in
+        self.world = _dist.world_size(group) if group is not None else 1
         self.n_stats = int(self.lib.tip_stats_len(self.P, self.K))
         with torch.cuda.device(self.device):
             self.theta = torch.empty(self.P * self.K, dtype=torch.float64, device=self.device)
