@@ -294,10 +294,13 @@ def run_ours(args):
         flops = 6.0 * K ** 3 * L_local
         achieved = flops / (kernel_ms * 1e-3) / 1e12
         peaks = _read_peaks()
+        prof = _read_profile()
         line["roofline"] = {
             "bound": "fp64_fma", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s", "frac": achieved / peak64,
-            "traffic": None, "kernel": "em_fused_kernel<10>", "kernel_ms": kernel_ms,
-            "flops_per_link_update": 6 * K ** 3, "peak_source": "tip_measure_fma_peak(DFMA) in this run",
+            "traffic": prof.get("traffic_bytes"), "kernel": "tip_em_step: em_fused_kernel<10> (87 % of the step) + em_finalize_kernel<10>",
+            "kernel_ms": kernel_ms, "flops_per_link_update": 6 * K ** 3,
+            "peak_source": "tip_measure_fma_peak(DFMA) measured in this run (no fp64 figure in MEASURED_PEAKS.json)",
+            "ncu_fp64_pipe_pct": prof.get("fp64_pipe_pct"), "ncu_source": prof.get("source"),
             "fp32_fma_peak": peak32,
             "hbm": {"algorithmic_bytes": 16 * n_rows, "achieved_gbs": 16 * n_rows / (kernel_ms * 1e-3) / 1e9,
                     "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json" if peaks else "absent"},
@@ -339,6 +342,19 @@ def _measure_peak(lib, kind):
     if rc != 0:
         raise RuntimeError("tip_measure_fma_peak failed: %s" % lib.tip_last_error())
     return out.value
+
+
+def _read_profile():
+    """dram traffic / fp64 pipe utilisation of the fused kernel from the committed ncu capture (per launch)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_em_fused_k10_metrics.json")) as fh:
+            m = json.load(fh)
+        rd = float(m["dram__bytes_read.sum"][0]) * {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}[m["dram__bytes_read.sum"][1]]
+        wr = float(m["dram__bytes_write.sum"][0]) * {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}[m["dram__bytes_write.sum"][1]]
+        return {"traffic_bytes": rd + wr, "source": "profiles/r1_em_fused_k10_metrics.json",
+                "fp64_pipe_pct": float(m["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"][0])}
+    except Exception:  # noqa: BLE001
+        return {}
 
 
 def _read_peaks():
