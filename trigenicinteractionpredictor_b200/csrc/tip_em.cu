@@ -53,8 +53,12 @@ struct EmCfg {
     static constexpr int NG = (32 / K) < K ? (32 / K) : K;
     static constexpr int CB = (K + NG - 1) / NG;
     static constexpr int NGU = (K + CB - 1) / CB;            // groups actually needed
+    // contribution buffer row: [ca|cb|cc] for K <= 4, [cb|cc] otherwise (slot a comes from M_g); stride == 2 (mod 4)
+    static constexpr int CSLOTS = kPrivateS ? 3 : 2;
+    static constexpr int CA = kPrivateS ? KP : 0;            // offset of cb inside a row
+    static constexpr int RC = CSLOTS * KP + (((CSLOTS * KP) % 4 == 2) ? 0 : 2);
     // shared memory of one warp-CTA: NBUF theta stages + contribution buffer (doubles), then ids (NBUF x 32 int4)
-    static constexpr int WARP_DBL = (NBUF + 1) * 32 * RS;
+    static constexpr int WARP_DBL = NBUF * 32 * RS + 32 * RC;
     static constexpr size_t SMEM = (size_t)WARP_DBL * 8 + NBUF * 32 * 16;
 };
 
@@ -145,12 +149,12 @@ __global__ void __launch_bounds__(32, MINB)
                     int p_slot, double *__restrict__ stats, double *__restrict__ Mg, int dbg)
 {
     using C = EmCfg<K, NBUF>;
-    constexpr int KP = C::KP, RS = C::RS, K3 = C::K3, CB = C::CB;
+    constexpr int KP = C::KP, RS = C::RS, K3 = C::K3, CB = C::CB, RC = C::RC, CA = C::CA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x;
     double *stage0 = reinterpret_cast<double *>(smem_raw);    // [NBUF][32][RS]
-    double *cbuf = stage0 + NBUF * 32 * RS;                   // [32][RS]
-    int4 *ids_sm = reinterpret_cast<int4 *>(cbuf + 32 * RS);  // [NBUF][32]
+    double *cbuf = stage0 + NBUF * 32 * RS;                   // [32][RC]
+    int4 *ids_sm = reinterpret_cast<int4 *>(cbuf + 32 * RC);  // [NBUF][32]
 
     // Tile bookkeeping (t, W, the rating of a tile, the p index) must stay on the uniform datapath.
     // ptxas gives every value ONE home: a single per-lane use of %ctaid.x / %nctaid.x (the row pointers
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(32, MINB)
         const int idx = ph * 32 + lane;
         const int l = idx / (2 * K), rem = idx - l * (2 * K);
         const int slot = 1 + rem / K, kk = rem % K;
-        sc_pack[ph] = (unsigned)(l * RS + slot * KP + kk) | ((unsigned)(l * 4 + slot) << 16) | ((unsigned)kk << 24);
+        sc_pack[ph] = (unsigned)(l * RC + CA + (slot - 1) * KP + kk) | ((unsigned)(l * 4 + slot) << 16) | ((unsigned)kk << 24);
     }
 
     // K <= 4 only: thread-private S
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(32, MINB)
         {
             if constexpr (K % 2 == 0) bulk_wait_read();  // the previous tile's bulk reductions have read cbuf
             double *row = stage + lane * RS;
-            double *crow = cbuf + lane * RS;
+            double *crow = cbuf + lane * RC;
             const int pbase = p_slot * kPSlotDoubles + r * (K * K * KP);
             double tb[KP], tc[KP], v[K], w[KP];
 #pragma unroll
@@ -289,6 +293,8 @@ __global__ void __launch_bounds__(32, MINB)
             double dsum = 0.0;
             const double *ta_p = row;  // walked separately so that `a` only ever indexes the constant bank
             double *tt_p = crow;
+            // (A per-lane ld.const prefetch of the next a-slice was tried against the 88 % constant-cache hit rate
+            // ncu reports: the divergent constant access serialises and costs 35 % - not kept.)
 #pragma unroll 1
             for (int a = 0; a < K; ++a) {
                 const double ta = *ta_p++;
@@ -318,7 +324,12 @@ __global__ void __launch_bounds__(32, MINB)
                 if constexpr (C::kPrivateS) *tt_p++ = tt;  // slot-a contribution (K >= 5: from M_g in em_finalize_kernel)
             }
             const double d = TIP_EPS + dsum;
-            const double s = cnt / d;
+            // s = cnt / d.  d lies in [1e-10, ~1]: an fp32 reciprocal seed and two Newton steps give 1/d to the
+            // last ulp or two (far inside the 1e-9 budget) in ~8 instructions instead of the ~30 of an IEEE divide
+            double rd = (double)__frcp_rn((float)d);
+            rd = rd * fma(-d, rd, 2.0);
+            rd = rd * fma(-d, rd, 2.0);
+            const double s = cnt * rd;
             if constexpr (LL) ll += cnt * log(d);  // by-product, only on request (TIP_EM_WITH_LOGLIK)
             // contributions of slot b and slot c; s*th_c into the stage for phase B
 #pragma unroll
@@ -329,9 +340,9 @@ __global__ void __launch_bounds__(32, MINB)
                     *reinterpret_cast<double2 *>(crow + k) = ca;
                 }
                 const double vb1 = (k + 1 < K) ? v[k + 1] : 0.0;
-                *reinterpret_cast<double2 *>(crow + KP + k) = make_double2(s * tb[k] * v[k], s * tb[k + 1] * vb1);
+                *reinterpret_cast<double2 *>(crow + CA + k) = make_double2(s * tb[k] * v[k], s * tb[k + 1] * vb1);
                 const double sc0 = s * tc[k], sc1 = s * tc[k + 1];
-                *reinterpret_cast<double2 *>(crow + 2 * KP + k) = make_double2(sc0 * w[k], sc1 * w[k + 1]);
+                *reinterpret_cast<double2 *>(crow + CA + KP + k) = make_double2(sc0 * w[k], sc1 * w[k + 1]);
                 *reinterpret_cast<double2 *>(row + 2 * KP + k) = make_double2(sc0, sc1);
             }
             if constexpr (C::kPrivateS) {
@@ -371,19 +382,19 @@ __global__ void __launch_bounds__(32, MINB)
                             acc = 0.0;
                             g = gl;
                         }
-                        acc += cbuf[l * RS + k];
+                        acc += cbuf[l * RC + k];
                     }
                     red_add_f64_nz(stats + (int64_t)g * K + k, acc);
                 }
             }
             // slots b, c
-            if constexpr (K % 2 == 0) {
+            if (K % 2 == 0 && !(dbg & 4)) {
                 // one bulk add-reduction per (link, slot): the 8K-byte row goes to the TMA unit
                 fence_async_smem();
                 if (cnt != 0.0) {
-                    const double *crow = cbuf + lane * RS;
-                    bulk_red_add_f64(stats + (int64_t)me.y * K, crow + KP, K * 8);
-                    bulk_red_add_f64(stats + (int64_t)me.z * K, crow + 2 * KP, K * 8);
+                    const double *crow = cbuf + lane * RC + CA;
+                    bulk_red_add_f64(stats + (int64_t)me.y * K, crow, K * 8);
+                    bulk_red_add_f64(stats + (int64_t)me.z * K, crow + KP, K * 8);
                 }
                 bulk_commit();
             } else {
@@ -399,7 +410,7 @@ __global__ void __launch_bounds__(32, MINB)
                         const int g = ib[(pk >> 16) & 0xffu];
                         red_add_f64_nz(stats + (int64_t)g * K + (pk >> 24), val);
                     }
-                    cb += SM::LPP * RS;
+                    cb += SM::LPP * RC;
                     ib += SM::LPP * 4;
                 }
             }
@@ -565,7 +576,7 @@ static int em_variant()
     if (v < 0) {
         const char *e = getenv("TIP_EM_VARIANT");
         v = e ? atoi(e) : 0;
-        if (v < 0 || v > 3) v = 0;
+        if (v < 0 || v > 4) v = 0;
     }
     return v;
 }
@@ -648,6 +659,7 @@ static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_ro
             case 1: rc = launch_variant<K, 2, 8, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
             case 2: rc = launch_variant<K, 2, 12, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
             case 3: rc = launch_variant<K, 1, 16, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
+            case 4: rc = launch_variant<K, 1, 14, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
             default: rc = launch_variant<K, 1, 12, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
         }
     }
