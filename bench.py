@@ -204,10 +204,11 @@ def run_ours(args):
     else:
         L_local, L_total, scaling = L_PER_GPU, L_PER_GPU * world, "weak"
         workload = ("cfg2: 6000 genes x 1M triplets, K=10, fold-1 train split = 800,000 links per GPU"
-                    + ("" if world == 1 else "; %d link shards, allreduce of statistics per iteration" % world))
+                    + ("" if world == 1 else "; %d link shards, statistics summed across ranks every iteration (%s)" % (
+                        world, "NVLink peer memory, fused into the M-step kernel" if args.exchange == "peer" else "NCCL allreduce")))
 
     group = torch.distributed.group.WORLD if world > 1 else None
-    eng = EMEngine(P, K, device=dev, group=group)
+    eng = EMEngine(P, K, device=dev, group=group, exchange=args.exchange)
     g1, g2, g3, lab = synth.planted_links_soa(P, L_local, seed=100 + rank, device=dev)
     g1[:P] = torch.arange(P, dtype=torch.int32, device=dev)            # every gene has a training link
     eng.set_train_links(g1, g2, g3, 1 - lab, lab)
@@ -223,15 +224,17 @@ def run_ours(args):
     def flush_l2():
         flush.zero_()
 
-    # one iteration captured in a CUDA graph (E-step, allreduce, M-step)
-    eng.em_iteration()
-    torch.cuda.synchronize(dev)
-    graph = torch.cuda.CUDAGraph()
-    before = eng.launches
-    with torch.cuda.graph(graph):
-        eng.em_iteration()
-    launches_per_step = eng.launches - before
+    # one iteration captured in a CUDA graph (E-step, statistics exchange, M-step); two graphs when the
+    # statistics are double-buffered for the peer-memory exchange
+    eng.capture_graphs()
+    launches_per_step = eng._graph_launches
     eng.set_params(theta0, pr0)
+
+    class _Replay:
+        @staticmethod
+        def replay():
+            eng.graph_step()
+    graph = _Replay
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -393,7 +396,7 @@ def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
             th_h.view(-1).copy_(eng.theta, non_blocking=True)
             p_h.view(-1).copy_(eng.p, non_blocking=True)
             torch.cuda.synchronize(dev)
-        api = "EMEngine.em_iteration with pinned host copies (link-sharded, NCCL allreduce)"
+        api = "EMEngine.em_iteration with pinned host copies (link-sharded, %s exchange)" % args.exchange
     for _ in range(3):
         step()
     tdist.barrier(group)
@@ -416,6 +419,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=["cfg2", "cfg4"], default="cfg2")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
+                    help="N>1: how link-shard statistics are summed (NVLink peer memory fused into the M-step, or NCCL)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

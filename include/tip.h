@@ -117,6 +117,23 @@ int tip_metrics(const double *d_scores, const int32_t *d_labels, int64_t T, int6
 int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t n_rows, int64_t n_rows_r0,
                            const int32_t *h_deg, double *h_theta, double *h_p, int n_iter, unsigned flags);
 
+/* ---- link shards over NVLink peer memory (replaces the NCCL allreduce between E-step and M-step) ----
+ * One process per GPU.  Each rank shares its statistics buffers and a flag array with its peers:
+ *   tip_ipc_export(d_ptr, handle[64], &offset)    on the owner; handle+offset travel over any host channel
+ *   tip_ipc_import(handle, offset, &d_peer_ptr)   on each peer: a pointer usable in kernels (P2P over NVLink)
+ * Per iteration i (statistics double-buffered by the caller, buffer i & 1):
+ *   tip_em_step(... d_stats = own buffer i&1 ...)
+ *   tip_peer_barrier(h_flag_ptrs, d_epoch, rank, nranks)   every rank has finished writing buffer i&1
+ *   tip_normalise_peers(P, K, h_stats_ptrs, nranks, ...)   M-step of the sum, in rank order, of all buffers i&1
+ * h_flag_ptrs[r] / h_stats_ptrs[r]: HOST arrays of nranks DEVICE pointers (own memory at index `rank`);
+ * a flag array is nranks uint64 initialised to 0; d_epoch is one local uint64 initialised to 0.
+ * The barrier kernel spins on flags written by other GPUs: run one rank per GPU, never two ranks on one GPU. */
+int tip_ipc_export(const void *d_ptr, void *h_handle64, int64_t *h_offset);
+int tip_ipc_import(const void *h_handle64, int64_t offset, void **d_ptr_out);
+int tip_peer_barrier(void *const *h_flag_ptrs, void *d_epoch, int rank, int nranks, void *stream);
+int tip_normalise_peers(int P, int K, void *const *h_stats_ptrs, int nranks, const int32_t *d_deg, double *d_theta,
+                        double *d_p, void *stream);
+
 /* ---- roofline denominators: measured FMA peak of this GPU ----
  * kind 0: fp64 DFMA, 1: fp32 FFMA, 2: fp64 mma.sync (DMMA m8n8k4), 3: DFMA and DMMA interleaved.
  * Returns TFLOP/s (2 flops per FMA) in *tflops; runs on the current device, synchronous. */

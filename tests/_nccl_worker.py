@@ -23,15 +23,18 @@ def main(out_dir):
     pr = rng.random((K, K, K, 2))
     pr /= pr.sum(axis=3, keepdims=True)
     lo, hi = tdist.shard_bounds(L, rk, w)
-    eng = EMEngine(P, K, device=dev, group=torch.distributed.group.WORLD)
-    eng.set_train_links(g[lo:hi, 0], g[lo:hi, 1], g[lo:hi, 2], 1 - lab[lo:hi], lab[lo:hi])   # deg is allreduced inside
-    eng.set_params(theta, pr)
-    print(rk, "links set", flush=True)
-    eng.em_iterations(5, use_graph=True)
-    th, p = eng.get_params()
-    ll = eng.loglik("train")
-    print(rk, "sharded iterations done", ll, flush=True)
-    np.savez(os.path.join(out_dir, "r%d.npz" % rk), th=th, p=p, ll=ll)
+    for exchange in ("nccl", "peer"):
+        eng = EMEngine(P, K, device=dev, group=torch.distributed.group.WORLD, exchange=exchange)
+        eng.set_train_links(g[lo:hi, 0], g[lo:hi, 1], g[lo:hi, 2], 1 - lab[lo:hi], lab[lo:hi])   # deg is allreduced inside
+        eng.set_params(theta, pr)
+        print(rk, exchange, "links set", flush=True)
+        eng.em_iterations(5, use_graph=True)
+        th, p = eng.get_params()
+        ll = eng.loglik("train")
+        if eng.peer is not None:
+            eng.peer.check()
+        print(rk, exchange, "sharded iterations done", ll, flush=True)
+        np.savez(os.path.join(out_dir, "r%d_%s.npz" % (rk, exchange)), th=th, p=p, ll=ll)
     if rk == 0:
         ref = EMEngine(P, K, device=dev)
         ref.set_train_links(g[:, 0], g[:, 1], g[:, 2], 1 - lab, lab)

@@ -1,5 +1,6 @@
-"""Link-sharded data parallelism over NCCL (needs >= 2 GPUs; skipped otherwise): two ranks, each with half of the
-links, one allreduce of the statistics per iteration, must reproduce the single-GPU iteration."""
+"""Link-sharded data parallelism (needs >= 2 GPUs; skipped otherwise): two ranks, each with half of the links, the
+statistics summed every iteration - once with an NCCL allreduce, once through NVLink peer memory fused into the
+M-step kernel - must reproduce the single-GPU iteration."""
 import os
 import subprocess
 import sys
@@ -22,8 +23,12 @@ def test_two_rank_link_shards_match_single_gpu(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     one = np.load(tmp_path / "single.npz")
-    for r in range(2):
-        got = np.load(tmp_path / ("r%d.npz" % r))
-        np.testing.assert_allclose(got["th"], one["th"], rtol=1e-10)
-        np.testing.assert_allclose(got["p"], one["p"], rtol=1e-10)
-        assert got["ll"] == pytest.approx(float(one["ll"]), rel=1e-11)
+    for exchange in ("nccl", "peer"):
+        for r in range(2):
+            got = np.load(tmp_path / ("r%d_%s.npz" % (r, exchange)))
+            np.testing.assert_allclose(got["th"], one["th"], rtol=1e-10)
+            np.testing.assert_allclose(got["p"], one["p"], rtol=1e-10)
+            assert got["ll"] == pytest.approx(float(one["ll"]), rel=1e-11)
+    # the peer-memory exchange adds the shards in rank order on every rank: replicas are bit-identical
+    a, b = np.load(tmp_path / "r0_peer.npz"), np.load(tmp_path / "r1_peer.npz")
+    assert np.array_equal(a["th"], b["th"]) and np.array_equal(a["p"], b["p"])

@@ -22,7 +22,9 @@ __global__ void __launch_bounds__(128) phase_a_probe(const double *__restrict__ 
     double acc = 0;
     for (int pass = 0; pass < passes; ++pass) {
 #pragma unroll 1
-        for (int a = 0; a < K; ++a) {
+        for (int a0 = 0; a0 < K; ++a0) {
+            // MODE 3: every CTA starts its sweep over p at a different slice (warps out of phase)
+            const int a = (MODE == 3) ? (a0 + blockIdx.x) % K : a0;
             const double ta = tc[0] + pass + a;
             double u = 0;
 #pragma unroll
@@ -32,7 +34,7 @@ __global__ void __launch_bounds__(128) phase_a_probe(const double *__restrict__ 
 #pragma unroll
                 for (int c = 0; c < K; c += 2) {
                     double p0, p1;
-                    if (MODE == 0) {
+                    if (MODE == 0 || MODE == 2) {
                         const double2 pv = *reinterpret_cast<const double2 *>(sp + (a * K + b) * K + c);
                         p0 = pv.x; p1 = pv.y;
                     } else {
@@ -98,6 +100,11 @@ int main()
     for (int wps : {4, 8, 12, 16, 20}) {
         run<0>(gp, out, wps / 4, 128);
         run<1>(gp, out, wps / 4, 128);
+    }
+    printf("single-warp CTAs, in phase (mode 1) vs out of phase (mode 3):\n");
+    for (int wps : {8, 12, 16}) {
+        run<1>(gp, out, wps, 32);
+        run<3>(gp, out, wps, 32);
     }
     dfma_latency_probe<<<1, 32>>>(out, cyc, 1000);
     cudaDeviceSynchronize();

@@ -73,3 +73,50 @@ def max_over_ranks(x: float, device=None, group=None) -> float:
     t = torch.tensor([x], dtype=torch.float64, device=device)
     td.all_reduce(t, op=td.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+class PeerExchange:
+    """Statistics exchange over NVLink peer memory (tip_peer_barrier + tip_normalise_peers) instead of an NCCL
+    allreduce.  Each rank owns one device buffer `[2][n_pad] doubles | world uint64 flags`; CUDA IPC handles are
+    swapped once through the process group, after which every rank holds a device pointer to every peer's buffer.
+    Iteration i uses statistics buffer i & 1 (double buffering makes one barrier per iteration sufficient)."""
+
+    def __init__(self, n_stats: int, device, group):
+        import ctypes
+        from . import _cabi
+        self.lib = _cabi.load()
+        self.group = group
+        self.world, self.rank = td.get_world_size(group), td.get_rank(group)
+        self.n_stats = n_stats
+        self.n_pad = (n_stats + 31) // 32 * 32
+        self.buf = torch.zeros(2 * self.n_pad + self.world, dtype=torch.float64, device=device)
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        handle = (ctypes.c_char * 64)()
+        off = ctypes.c_int64(0)
+        _cabi.check(self.lib.tip_ipc_export(ctypes.c_void_p(self.buf.data_ptr()), handle, ctypes.byref(off)),
+                    "tip_ipc_export")
+        mine = (bytes(handle.raw), int(off.value))
+        everyone = [None] * self.world
+        td.all_gather_object(everyone, mine, group=group)
+        bases = []
+        for r, (h, o) in enumerate(everyone):
+            if r == self.rank:
+                bases.append(self.buf.data_ptr())
+            else:
+                out = ctypes.c_void_p(0)
+                hb = ctypes.create_string_buffer(h, 64)
+                _cabi.check(self.lib.tip_ipc_import(hb, ctypes.c_int64(o), ctypes.byref(out)), "tip_ipc_import")
+                bases.append(out.value)
+        arr = ctypes.c_void_p * self.world
+        self.stats_ptrs = [arr(*[b + i * self.n_pad * 8 for b in bases]) for i in range(2)]
+        self.flag_ptrs = arr(*[b + 2 * self.n_pad * 8 for b in bases])
+        torch.cuda.synchronize(device)
+        td.barrier(group=group)          # every rank has mapped every buffer before anyone signals
+
+    def stats(self, parity: int) -> torch.Tensor:
+        return self.buf[parity * self.n_pad: parity * self.n_pad + self.n_stats]
+
+    def check(self):
+        """Raises if a barrier timed out (a peer stopped participating)."""
+        if int(self.epoch.item()) == -1:
+            raise RuntimeError("tip_peer_barrier timed out: a peer rank stopped participating")

@@ -31,7 +31,8 @@ class PackedLinks:
 
 
 class EMEngine:
-    def __init__(self, P: int, K: int, device=None, group=None, flags: int = _cabi.TIP_EM_DEFAULT):
+    def __init__(self, P: int, K: int, device=None, group=None, flags: int = _cabi.TIP_EM_DEFAULT,
+                 exchange: str = "peer"):
         if not torch.cuda.is_available():
             raise _cabi.TipLibraryError("no CUDA device: trigenicinteractionpredictor_b200 has no CPU path")
         self.lib = _cabi.load()
@@ -48,11 +49,18 @@ class EMEngine:
             self.stats = torch.zeros(self.n_stats, dtype=torch.float64, device=self.device)
             self.ll_out = torch.zeros(1, dtype=torch.float64, device=self.device)
             self.ll_ws = torch.empty(int(self.lib.tip_loglik_workspace_bytes()), dtype=torch.uint8, device=self.device)
+        # link shards: how the statistics are summed across ranks - "peer" (NVLink peer memory, fused into the
+        # M-step kernel) or "nccl" (torch.distributed allreduce)
+        self.peer = None
+        self._iter = 0
+        if self.world > 1 and exchange == "peer":
+            with torch.cuda.device(self.device):
+                self.peer = _dist.PeerExchange(self.n_stats, self.device, group)
         self.train: PackedLinks | None = None
         self.test: PackedLinks | None = None
         self.test_ids = None      # (g1, g2, g3, labels) int32 tensors in test order
         self.em_ws = None
-        self._graph = None
+        self._graphs = None
         self._graph_key = None
         self.launches = 0         # kernel launches issued by libtip on behalf of this engine
 
@@ -96,7 +104,7 @@ class EMEngine:
                         "tip_em_workspace_bytes")
             self.em_ws = torch.empty(max(nb.value, 8), dtype=torch.uint8, device=self.device)
             self.em_ws_bytes = nb.value
-        self._graph = None
+        self._graphs = None
 
     def set_test_links(self, g1, g2, g3, n0, n1):
         self.test = self.pack(g1, g2, g3, n0, n1, want_deg=False)
@@ -123,11 +131,12 @@ class EMEngine:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def em_step(self):
-        """E-step statistics of this rank's rows into self.stats (no normalisation)."""
+    def em_step(self, stats=None):
+        """E-step statistics of this rank's rows into `stats` (default self.stats); no normalisation."""
         t = self.train
+        stats = self.stats if stats is None else stats
         _cabi.check(self.lib.tip_em_step(self.P, self.K, _ptr(t.rows), t.n_rows, t.n_rows_r0, _ptr(self.theta),
-                                         _ptr(self.p), _ptr(self.stats), _ptr(self.em_ws), self.em_ws_bytes,
+                                         _ptr(self.p), _ptr(stats), _ptr(self.em_ws), self.em_ws_bytes,
                                          self.flags, self._stream()), "tip_em_step")
         self.launches += 3 if (4 < self.K <= 10 and not (self.flags & _cabi.TIP_EM_FORCE_GENERIC)) else 2
 
@@ -138,36 +147,59 @@ class EMEngine:
 
     def em_iteration(self):
         """One make_iteration: E-step, sum of statistics over link shards, M-step."""
+        if self.peer is not None:
+            par = self._iter & 1
+            self._iter += 1
+            self.em_step(self.peer.stats(par))
+            _cabi.check(self.lib.tip_peer_barrier(self.peer.flag_ptrs, _ptr(self.peer.epoch), self.peer.rank,
+                                                  self.peer.world, self._stream()), "tip_peer_barrier")
+            _cabi.check(self.lib.tip_normalise_peers(self.P, self.K, self.peer.stats_ptrs[par], self.peer.world,
+                                                     _ptr(self.train.deg), _ptr(self.theta), _ptr(self.p),
+                                                     self._stream()), "tip_normalise_peers")
+            self.launches += 2
+            return
         self.em_step()
         if self.world > 1:
             _dist.allreduce_sum_(self.stats, self.group)
         self.normalise()
 
-    def em_iterations(self, n: int, use_graph: bool = True):
-        """n iterations; the (E-step, allreduce, M-step) body is captured once in a CUDA graph and replayed
-        (an iteration at K=10 on 1e6 links is a few hundred microseconds, so launch latency matters)."""
-        if n <= 0:
-            return
-        if not use_graph or n < 3:
-            for _ in range(n):
-                self.em_iteration()
-            return
-        key = (self.train.rows.data_ptr(), self.train.n_rows, self.flags)
-        if self._graph is None or self._graph_key != key:
-            with torch.cuda.device(self.device):
-                self.em_iteration()                       # warm-up outside capture (sets func attributes, NCCL)
-                n -= 1
-                torch.cuda.synchronize(self.device)
+    # ---- CUDA-graph replay of whole iterations (two graphs when the statistics are double-buffered) ----
+    def capture_graphs(self):
+        with torch.cuda.device(self.device):
+            self.em_iteration()                           # warm-up outside capture (function attributes, NCCL)
+            torch.cuda.synchronize(self.device)
+            self._graphs, self._graph_launches = [], 0
+            for _ in range(2 if self.peer is not None else 1):
                 g = torch.cuda.CUDAGraph()
                 before = self.launches
                 with torch.cuda.graph(g):
                     self.em_iteration()
                 self._graph_launches = self.launches - before
                 self.launches = before
-                self._graph, self._graph_key = g, key
+                self._graphs.append(g)
+            self._gpos = 0
+            self._graph_key = (self.train.rows.data_ptr(), self.train.n_rows, self.flags)
+
+    def graph_step(self):
+        self._graphs[self._gpos % len(self._graphs)].replay()
+        self._gpos += 1
+        self.launches += self._graph_launches
+
+    def em_iterations(self, n: int, use_graph: bool = True):
+        """n iterations; the (E-step, exchange, M-step) body is captured once in a CUDA graph and replayed
+        (an iteration at K=10 on 1e6 links is a few hundred microseconds, so launch latency matters)."""
+        if n <= 0:
+            return
+        if not use_graph or n < 4:
+            for _ in range(n):
+                self.em_iteration()
+            return
+        key = (self.train.rows.data_ptr(), self.train.n_rows, self.flags)
+        if getattr(self, "_graphs", None) is None or self._graph_key != key:
+            self.capture_graphs()
+            n -= 1                                        # the warm-up iteration of capture_graphs counted
         for _ in range(n):
-            self._graph.replay()
-            self.launches += self._graph_launches
+            self.graph_step()
 
     # ------------------------------------------------------------------ likelihood / scoring / metrics
     def loglik(self, which: str = "train") -> float:
@@ -183,7 +215,10 @@ class EMEngine:
         return float(self.ll_out.item())
 
     def step_loglik(self) -> float:
-        """log-likelihood by-product of the last E-step (of the parameters that step started from)."""
+        """log-likelihood by-product of the last E-step of THIS rank's rows (of the parameters that step started
+        from); needs TIP_EM_WITH_LOGLIK on the K-specialised path."""
+        if self.peer is not None:
+            return float(self.peer.stats((self._iter - 1) & 1)[-1].item())
         return float(self.stats[-1].item())
 
     def scores(self) -> torch.Tensor:
