@@ -311,6 +311,27 @@ def run_ours(args):
     else:
         line["roofline"] = None
 
+    # ---- fp32-compute / fp64-accumulate mode (north_star's 1e-5 mode), same workload, informational ----
+    if world == 1:
+        eng32 = EMEngine(P, K, device=dev, flags=_cabi.TIP_EM_FP32_COMPUTE)
+        eng32.train, eng32.em_ws, eng32.em_ws_bytes = eng.train, eng.em_ws, eng.em_ws_bytes
+        eng32.set_params(theta0, pr0)
+        eng32.capture_graphs()
+        for _ in range(3):
+            flush_l2()
+            eng32.graph_step()
+        t32 = 0.0
+        for _ in range(args.steps):
+            flush_l2()
+            a.record()
+            eng32.graph_step()
+            b.record()
+            torch.cuda.synchronize(dev)
+            t32 += a.elapsed_time(b)
+        line["value_fp32_compute"] = L_total / (t32 / args.steps * 1e-3)
+        line["fp32_compute_roofline_frac"] = (6.0 * K ** 3 * L_local / (t32 / args.steps * 1e-3) / 1e12) / peak32 if rank == 0 else None
+        del eng32
+
     # ---- end to end through host buffers ----
     e2e = _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist)
     line["e2e"] = e2e

@@ -47,7 +47,8 @@ extern "C" {
 /* flags for tip_em_step */
 #define TIP_EM_DEFAULT 0u
 #define TIP_EM_FORCE_GENERIC 1u /* use the any-K kernels even where a K-specialised kernel exists */
-#define TIP_EM_FP32_COMPUTE 2u  /* fp32 products / fp64 accumulation (1e-5 mode); not in ABI v1 kernels yet */
+#define TIP_EM_FP32_COMPUTE 2u  /* K <= 10: the two K^3 contractions of the E-step in fp32 (FFMA), everything that
+                                   is accumulated across links in fp64; results within 1e-5 of the fp64 mode */
 #define TIP_EM_WITH_LOGLIK 4u   /* also accumulate the log-likelihood by-product (last stats slot); off by
                                    default because the log costs ~2 % of a K=10 step and the training loop only
                                    needs the likelihood every `fcheck` iterations (tip_loglik) */

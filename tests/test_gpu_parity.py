@@ -99,6 +99,35 @@ def test_duplicates_conflicts_and_string_sorted_slots(torch_cuda, flags):
     assert m.calculate_metrics()[3] == pytest.approx(tr["metrics"][3], abs=1e-6)
 
 
+@pytest.mark.parametrize("K", [2, 3, 10])
+def test_fp32_compute_mode_within_1e5(torch_cuda, K):
+    """TIP_EM_FP32_COMPUTE: fp32 contractions, fp64 accumulation - theta, p, log-likelihood per iteration within
+    1e-5 relative of the reference (north_star tolerance for this mode), AUC within 1e-6."""
+    tr = np.load(os.path.join(BASE, "trace_K%d.npz" % K))
+    m = _model(BASE, "train1.dat", "test1.dat", flags=2)
+    random.seed(1000)
+    m.initialize_parameters(K)
+    for it in range(5):
+        m.make_iteration()
+        assert _relerr(m.theta, tr["theta%d" % (it + 1)]) < 1e-5, "theta iteration %d" % (it + 1)
+        assert _relerr(m.pr, tr["pr%d" % (it + 1)]) < 1e-5, "p iteration %d" % (it + 1)
+        assert m.compute_likelihood() == pytest.approx(tr["loglik"][it + 1], rel=1e-5)
+    m.calculate_test_set_results()
+    assert _relerr(m._scores.cpu().numpy(), tr["scores_test_order"]) < 1e-5
+    assert m.calculate_metrics()[3] == pytest.approx(tr["metrics"][3], abs=1e-6)
+
+
+def test_fp32_mode_is_rejected_where_it_does_not_exist(torch_cuda):
+    from trigenicinteractionpredictor_b200._cabi import TipLibraryError
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    g, n0, n1, theta, pr = _random_problem(100, 640, 12, 1)
+    eng = EMEngine(100, 12, flags=2)
+    eng.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+    eng.set_params(theta, pr)
+    with pytest.raises(TipLibraryError):
+        eng.em_step()
+
+
 def test_gene_seen_only_in_test_raises_like_reference(torch_cuda):
     m = _model(os.path.join(GOLDEN, "testonly"), "train.dat", "test.dat")
     random.seed(5)

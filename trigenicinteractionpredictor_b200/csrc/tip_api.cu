@@ -46,7 +46,8 @@ extern "C" int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int
                 "tip_em_step: n_rows (%lld) and n_rows_r0 (%lld) must be multiples of 32 from tip_pack_rows",
                 (long long)n_rows, (long long)n_rows_r0);
     TIP_REQUIRE(d_theta && d_p && d_stats && (d_rows || n_rows == 0), "tip_em_step: null pointer");
-    TIP_REQUIRE(!(flags & TIP_EM_FP32_COMPUTE), "tip_em_step: TIP_EM_FP32_COMPUTE is not implemented in ABI v%d", TIP_ABI_VERSION);
+    TIP_REQUIRE(!(flags & TIP_EM_FP32_COMPUTE) || (K <= 10 && !(flags & (TIP_EM_FORCE_GENERIC | TIP_EM_WITH_LOGLIK))),
+                "tip_em_step: TIP_EM_FP32_COMPUTE exists for the K <= 10 kernels only, without FORCE_GENERIC / WITH_LOGLIK");
     TIP_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * (size_t)tip_stats_len(P, K), st));
     if (n_rows == 0) return 0;
     const int4 *rows = reinterpret_cast<const int4 *>(d_rows);
@@ -56,7 +57,7 @@ extern "C" int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int
                     "tip_em_step: K=%d needs %zu bytes of workspace (got %zu), see tip_em_workspace_bytes", K, need, ws_bytes);
         bool handled = false;
         int rc = launch_em_tuned(P, K, rows, n_rows, n_rows_r0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws),
-                                 (flags & TIP_EM_WITH_LOGLIK) != 0, st, &handled);
+                                 (flags & TIP_EM_WITH_LOGLIK) != 0, (flags & TIP_EM_FP32_COMPUTE) != 0, st, &handled);
         if (rc != 0 || handled) return rc;
     }
     TIP_REQUIRE(d_ws != nullptr && ws_bytes >= (size_t)n_rows * sizeof(double),

@@ -62,14 +62,16 @@ struct EmCfg {
     static constexpr size_t SMEM = (size_t)WARP_DBL * 8 + NBUF * 32 * 16;
 };
 
-// p[abc][r] (reference layout) -> [r][ab][c padded] staging copy, then memcpy to the constant bank
-__global__ void stage_p_kernel(int K, int KP, const double *__restrict__ p, double *__restrict__ out)
+// p[abc][r] (reference layout) -> [r][ab][c padded] staging copy (fp64, or fp32 for the fp32-compute mode),
+// then memcpy to the constant bank
+template <typename T>
+__global__ void stage_p_kernel(int K, int KP, const double *__restrict__ p, T *__restrict__ out)
 {
     const int n = 2 * K * K * KP;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const int r = e / (K * K * KP), rem = e - r * (K * K * KP);
         const int pair = rem / KP, c = rem - pair * KP;
-        out[e] = (c < K) ? p[((int64_t)pair * K + c) * 2 + r] : 0.0;
+        out[e] = (c < K) ? (T)p[((int64_t)pair * K + c) * 2 + r] : (T)0;
     }
 }
 
@@ -143,7 +145,10 @@ struct ScatterMap {
     static constexpr int NPERIOD = G;   // periods per tile (32 / LPP)
 };
 
-template <int K, int NBUF, int MINB, bool LL>
+// T = double: the fp64 path (1e-9 parity).  T = float: fp32-compute / fp64-accumulate mode (TIP_EM_FP32_COMPUTE):
+// only the two K^3 contractions of phase A run in fp32 (FFMA, p as fp32 in the constant bank); the normaliser,
+// s, every contribution that leaves the thread, M_g and all statistics stay fp64 (1e-5 parity).
+template <int K, int NBUF, int MINB, bool LL, typename T>
 __global__ void __launch_bounds__(32, MINB)
     em_fused_kernel(int P, const int4 *__restrict__ rows, int n_tiles, int n_tiles_r0, const double *__restrict__ theta,
                     int p_slot, double *__restrict__ stats, double *__restrict__ Mg, int dbg)
@@ -278,52 +283,55 @@ __global__ void __launch_bounds__(32, MINB)
             if constexpr (K % 2 == 0) bulk_wait_read();  // the previous tile's bulk reductions have read cbuf
             double *row = stage + lane * RS;
             double *crow = cbuf + lane * RC;
-            const int pbase = p_slot * kPSlotDoubles + r * (K * K * KP);
-            double tb[KP], tc[KP], v[K], w[KP];
+            // p index in units of T inside this launch's constant-bank slot
+            const int pbase = p_slot * (kPSlotDoubles * (int)(sizeof(double) / sizeof(T))) + r * (K * K * KP);
+            const T *cp = reinterpret_cast<const T *>(c_pem);
+            T tb[KP], tc[KP], v[K], w[KP];
 #pragma unroll
             for (int k = 0; k < KP; k += 2) {
                 const double2 b2 = *reinterpret_cast<const double2 *>(row + KP + k);
                 const double2 c2 = *reinterpret_cast<const double2 *>(row + 2 * KP + k);
-                tb[k] = b2.x; tb[k + 1] = b2.y;
-                tc[k] = c2.x; tc[k + 1] = c2.y;
-                w[k] = 0.0; w[k + 1] = 0.0;
+                tb[k] = (T)b2.x; tb[k + 1] = (T)b2.y;
+                tc[k] = (T)c2.x; tc[k + 1] = (T)c2.y;
+                w[k] = (T)0; w[k + 1] = (T)0;
             }
 #pragma unroll
-            for (int k = 0; k < K; ++k) v[k] = 0.0;
-            double dsum = 0.0;
+            for (int k = 0; k < K; ++k) v[k] = (T)0;
+            T dsum = (T)0;
             const double *ta_p = row;  // walked separately so that `a` only ever indexes the constant bank
             double *tt_p = crow;
             // (A per-lane ld.const prefetch of the next a-slice was tried against the 88 % constant-cache hit rate
             // ncu reports: the divergent constant access serialises and costs 35 % - not kept.)
 #pragma unroll 1
             for (int a = 0; a < K; ++a) {
-                const double ta = *ta_p++;
+                const T ta = (T)(*ta_p++);
                 const int pa = pbase + a * (K * KP);
-                double u = 0.0;
+                T u = (T)0;
 #pragma unroll
                 for (int b = 0; b < K; ++b) {
-                    const double ab = ta * tb[b];
-                    double q0 = 0.0, q1 = 0.0;
+                    const T ab = ta * tb[b];
+                    T q0 = (T)0, q1 = (T)0;
 #pragma unroll
                     for (int c = 0; c < K; c += 2) {
-                        // (pa + b*KP + c) is even: one 16-byte uniform load feeds four DFMA
-                        const double2 pv = *reinterpret_cast<const double2 *>(&c_pem[pa + b * KP + c]);
-                        q0 = fma(pv.x, tc[c], q0);
-                        w[c] = fma(ab, pv.x, w[c]);
+                        // (pa + b*KP + c) is even: one uniform load feeds four FMA
+                        const T p0 = cp[pa + b * KP + c];
+                        q0 = fma(p0, tc[c], q0);
+                        w[c] = fma(ab, p0, w[c]);
                         if (c + 1 < K) {
-                            q1 = fma(pv.y, tc[c + 1], q1);
-                            w[c + 1] = fma(ab, pv.y, w[c + 1]);
+                            const T p1 = cp[pa + b * KP + c + 1];
+                            q1 = fma(p1, tc[c + 1], q1);
+                            w[c + 1] = fma(ab, p1, w[c + 1]);
                         }
                     }
-                    const double q = q0 + q1;
+                    const T q = q0 + q1;
                     u = fma(tb[b], q, u);
                     v[b] = fma(ta, q, v[b]);
                 }
-                const double tt = ta * u;
+                const T tt = ta * u;
                 dsum += tt;
-                if constexpr (C::kPrivateS) *tt_p++ = tt;  // slot-a contribution (K >= 5: from M_g in em_finalize_kernel)
+                if constexpr (C::kPrivateS) *tt_p++ = (double)tt;  // slot-a contribution (K >= 5: from M_g in em_finalize_kernel)
             }
-            const double d = TIP_EPS + dsum;
+            const double d = TIP_EPS + (double)dsum;
             // s = cnt / d.  d lies in [1e-10, ~1]: an fp32 reciprocal seed and two Newton steps give 1/d to the
             // last ulp or two (far inside the 1e-9 budget) in ~8 instructions instead of the ~30 of an IEEE divide
             double rd = (double)__frcp_rn((float)d);
@@ -339,10 +347,13 @@ __global__ void __launch_bounds__(32, MINB)
                     ca.x *= s; ca.y *= s;
                     *reinterpret_cast<double2 *>(crow + k) = ca;
                 }
-                const double vb1 = (k + 1 < K) ? v[k + 1] : 0.0;
-                *reinterpret_cast<double2 *>(crow + CA + k) = make_double2(s * tb[k] * v[k], s * tb[k + 1] * vb1);
-                const double sc0 = s * tc[k], sc1 = s * tc[k + 1];
-                *reinterpret_cast<double2 *>(crow + CA + KP + k) = make_double2(sc0 * w[k], sc1 * w[k + 1]);
+                // theta values re-read in fp64 from the stage (T = float only rounded them for the contractions)
+                const double2 b2 = *reinterpret_cast<const double2 *>(row + KP + k);
+                const double2 c2 = *reinterpret_cast<const double2 *>(row + 2 * KP + k);
+                const double vb1 = (k + 1 < K) ? (double)v[k + 1] : 0.0;
+                *reinterpret_cast<double2 *>(crow + CA + k) = make_double2(s * b2.x * (double)v[k], s * b2.y * vb1);
+                const double sc0 = s * c2.x, sc1 = s * c2.y;
+                *reinterpret_cast<double2 *>(crow + CA + KP + k) = make_double2(sc0 * (double)w[k], sc1 * (double)w[k + 1]);
                 *reinterpret_cast<double2 *>(row + 2 * KP + k) = make_double2(sc0, sc1);
             }
             if constexpr (C::kPrivateS) {
@@ -352,9 +363,10 @@ __global__ void __launch_bounds__(32, MINB)
                     const double ta = row[a];
 #pragma unroll
                     for (int b = 0; b < K; ++b) {
-                        const double sab = s * ta * tb[b];
+                        const double sab = s * ta * (double)tb[b];
 #pragma unroll
-                        for (int c = 0; c < K; ++c) Sacc[(a * K + b) * K + c] = fma(sab, tc[c], Sacc[(a * K + b) * K + c]);
+                        for (int c = 0; c < K; ++c)
+                            Sacc[(a * K + b) * K + c] = fma(sab, (double)tc[c], Sacc[(a * K + b) * K + c]);
                     }
                 }
             }
@@ -592,19 +604,19 @@ static int em_debug()
     return v;
 }
 
-template <int K, int NBUF, int MINB, bool LL>
+template <int K, int NBUF, int MINB, bool LL, typename T = double>
 static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, int slot,
                           double *stats, double *Mg, cudaStream_t st)
 {
     using C = EmCfg<K, NBUF>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)C::SMEM));
-        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL>,
+        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL, T>,
                                             cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int nb = 0;
-        TIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, em_fused_kernel<K, NBUF, MINB, LL>, 32, C::SMEM));
+        TIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, em_fused_kernel<K, NBUF, MINB, LL, T>, 32, C::SMEM));
         TIP_REQUIRE(nb >= 1, "em_fused_kernel<%d> does not fit on an SM (smem %zu)", K, C::SMEM);
         blocks_per_sm = nb;
     }
@@ -613,7 +625,7 @@ static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_row
     int64_t cap = (int64_t)sm_count() * blocks_per_sm;
     int grid = (int)(n_tiles < cap ? n_tiles : cap);
     if (grid < 1) grid = 1;
-    em_fused_kernel<K, NBUF, MINB, LL><<<grid, 32, C::SMEM, st>>>(P, rows, (int)n_tiles, (int)(n_rows_r0 / 32), theta, slot,
+    em_fused_kernel<K, NBUF, MINB, LL, T><<<grid, 32, C::SMEM, st>>>(P, rows, (int)n_tiles, (int)(n_rows_r0 / 32), theta, slot,
                                                                  stats, Mg, em_debug());
     TIP_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -626,16 +638,20 @@ size_t em_tuned_workspace_bytes(int P, int K)
 }
 
 // p -> E-step layout -> constant bank slot (stream-ordered); returns the slot in *slot_out
-static int upload_p_const(int K, const double *p, cudaStream_t st, int *slot_out)
+static int upload_p_const(int K, const double *p, cudaStream_t st, int *slot_out, bool f32 = false)
 {
     const int KP = K + (K & 1);
     static double *stage_ptr = nullptr;
     if (!stage_ptr) TIP_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&stage_ptr), g_pstage));
     const int slot = (g_slot_counter++) % kPSlots;
     const int n = 2 * K * K * KP;
-    stage_p_kernel<<<(n + 255) / 256, 256, 0, st>>>(K, KP, p, stage_ptr + slot * kPSlotDoubles);
+    double *dst = stage_ptr + slot * kPSlotDoubles;
+    if (f32)
+        stage_p_kernel<float><<<(n + 255) / 256, 256, 0, st>>>(K, KP, p, reinterpret_cast<float *>(dst));
+    else
+        stage_p_kernel<double><<<(n + 255) / 256, 256, 0, st>>>(K, KP, p, dst);
     TIP_CHECK_CUDA(cudaGetLastError());
-    TIP_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_pem, stage_ptr + slot * kPSlotDoubles, sizeof(double) * n,
+    TIP_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_pem, dst, (f32 ? sizeof(float) : sizeof(double)) * n,
                                            sizeof(double) * slot * kPSlotDoubles, cudaMemcpyDeviceToDevice, st));
     *slot_out = slot;
     return 0;
@@ -643,16 +659,18 @@ static int upload_p_const(int K, const double *p, cudaStream_t st, int *slot_out
 
 template <int K>
 static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
-                           const double *p, double *stats, double *ws, bool with_ll, cudaStream_t st)
+                           const double *p, double *stats, double *ws, bool with_ll, bool f32, cudaStream_t st)
 {
     int slot = 0;
     {
-        const int rc0 = upload_p_const(K, p, st, &slot);
+        const int rc0 = upload_p_const(K, p, st, &slot, f32);
         if (rc0 != 0) return rc0;
     }
     if (K > 4) TIP_CHECK_CUDA(cudaMemsetAsync(ws, 0, em_tuned_workspace_bytes(P, K), st));
     int rc;
-    if (with_ll) {
+    if (f32) {
+        rc = launch_variant<K, 1, 16, false, float>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st);
+    } else if (with_ll) {
         rc = launch_variant<K, 1, 12, true>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st);
     } else {
         switch (em_variant()) {
@@ -809,20 +827,20 @@ int launch_loglik_tuned(int K, const int4 *rows, int64_t n_rows, int64_t n_rows_
 }
 
 int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
-                    const double *p, double *stats, double *ws, bool with_ll, cudaStream_t st, bool *handled)
+                    const double *p, double *stats, double *ws, bool with_ll, bool f32, cudaStream_t st, bool *handled)
 {
     *handled = true;
     switch (K) {
-        case 1: return launch_em_fused<1>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
-        case 2: return launch_em_fused<2>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
-        case 3: return launch_em_fused<3>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
-        case 4: return launch_em_fused<4>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
-        case 5: return launch_em_fused<5>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
-        case 6: return launch_em_fused<6>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
-        case 7: return launch_em_fused<7>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
-        case 8: return launch_em_fused<8>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
-        case 9: return launch_em_fused<9>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
-        case 10: return launch_em_fused<10>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, st);
+        case 1: return launch_em_fused<1>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
+        case 2: return launch_em_fused<2>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
+        case 3: return launch_em_fused<3>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
+        case 4: return launch_em_fused<4>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
+        case 5: return launch_em_fused<5>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
+        case 6: return launch_em_fused<6>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
+        case 7: return launch_em_fused<7>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
+        case 8: return launch_em_fused<8>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
+        case 9: return launch_em_fused<9>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
+        case 10: return launch_em_fused<10>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
         default: *handled = false; return 0;
     }
 }
