@@ -101,10 +101,12 @@ extern "C" int tip_score(int P, int K, const int32_t *d_g1, const int32_t *d_g2,
 // host-buffer entry (grow-only device scratch, released with the process)
 // ---------------------------------------------------------------------------------------------
 namespace {
+constexpr int kHostChunks = 8;  // row chunks of the first iteration: H2D of chunk i+1 overlaps the E-step of chunk i
 struct HostPool {
     void *rows = nullptr, *theta = nullptr, *p = nullptr, *stats = nullptr, *deg = nullptr, *ws = nullptr;
     size_t rows_b = 0, theta_b = 0, p_b = 0, stats_b = 0, deg_b = 0, ws_b = 0;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, copy = nullptr;
+    cudaEvent_t ev[kHostChunks] = {};
 };
 HostPool g_pool;
 
@@ -126,7 +128,11 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
     TIP_REQUIRE(P > 0 && valid_K(K) && h_rows && h_deg && h_theta && h_p && n_iter >= 0 && n_rows >= 0,
                 "tip_em_iterations_host: bad arguments");
     HostPool &g = g_pool;
-    if (!g.st) TIP_CHECK_CUDA(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
+    if (!g.st) {
+        TIP_CHECK_CUDA(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
+        TIP_CHECK_CUDA(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
+        for (int c = 0; c < kHostChunks; ++c) TIP_CHECK_CUDA(cudaEventCreateWithFlags(&g.ev[c], cudaEventDisableTiming));
+    }
     const size_t nth = (size_t)P * K * 8, np = (size_t)2 * K * K * K * 8, nst = (size_t)tip_stats_len(P, K) * 8;
     size_t wsb = 0;
     if (tip_em_workspace_bytes(P, K, n_rows, flags, &wsb) != 0) return -1;
@@ -135,11 +141,45 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
         (rc = ensure(&g.p, &g.p_b, np)) || (rc = ensure(&g.stats, &g.stats_b, nst)) ||
         (rc = ensure(&g.deg, &g.deg_b, (size_t)P * 4)) || (rc = ensure(&g.ws, &g.ws_b, wsb)))
         return rc;
-    TIP_CHECK_CUDA(cudaMemcpyAsync(g.rows, h_rows, (size_t)n_rows * 16, cudaMemcpyHostToDevice, g.st));
     TIP_CHECK_CUDA(cudaMemcpyAsync(g.deg, h_deg, (size_t)P * 4, cudaMemcpyHostToDevice, g.st));
     TIP_CHECK_CUDA(cudaMemcpyAsync(g.theta, h_theta, nth, cudaMemcpyHostToDevice, g.st));
     TIP_CHECK_CUDA(cudaMemcpyAsync(g.p, h_p, np, cudaMemcpyHostToDevice, g.st));
-    for (int it = 0; it < n_iter; ++it) {
+    int it0 = 0;
+    const bool tuned = !(flags & TIP_EM_FORCE_GENERIC) && K <= 10;
+    if (tuned && n_iter > 0 && n_rows >= 32 * kHostChunks) {
+        // first iteration: rows arrive in chunks on the copy stream, the fused kernel consumes each chunk as
+        // soon as it has landed (statistics accumulate across the chunk launches)
+        const int4 *rows = reinterpret_cast<const int4 *>(g.rows);
+        const bool ll = (flags & TIP_EM_WITH_LOGLIK) != 0, f32 = (flags & TIP_EM_FP32_COMPUTE) != 0;
+        bool handled = false;
+        TIP_CHECK_CUDA(cudaMemsetAsync(g.stats, 0, nst, g.st));
+        rc = launch_em_tuned(P, K, rows, 0, 0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
+                             (double *)g.ws, ll, f32, g.st, &handled, 1);
+        if (rc) return rc;
+        const int64_t n_tiles = n_rows / 32, per = (n_tiles + kHostChunks - 1) / kHostChunks;
+        for (int c = 0; c < kHostChunks; ++c) {
+            const int64_t t0 = per * c, t1 = (t0 + per < n_tiles) ? t0 + per : n_tiles;
+            if (t0 >= t1) break;
+            TIP_CHECK_CUDA(cudaMemcpyAsync((char *)g.rows + t0 * 512, (const char *)h_rows + t0 * 512, (size_t)(t1 - t0) * 512,
+                                           cudaMemcpyHostToDevice, g.copy));
+            TIP_CHECK_CUDA(cudaEventRecord(g.ev[c], g.copy));
+            TIP_CHECK_CUDA(cudaStreamWaitEvent(g.st, g.ev[c], 0));
+            int64_t r0 = n_rows_r0 / 32 - t0;
+            r0 = r0 < 0 ? 0 : (r0 > t1 - t0 ? t1 - t0 : r0);
+            rc = launch_em_tuned(P, K, rows + t0 * 32, (t1 - t0) * 32, r0 * 32, (const double *)g.theta, (const double *)g.p,
+                                 (double *)g.stats, (double *)g.ws, ll, f32, g.st, &handled, 2);
+            if (rc) return rc;
+        }
+        rc = launch_em_tuned(P, K, rows, 0, 0, (const double *)g.theta, (const double *)g.p, (double *)g.stats, (double *)g.ws,
+                             ll, f32, g.st, &handled, 4);
+        if (rc) return rc;
+        rc = tip_normalise(P, K, (const double *)g.stats, (const int32_t *)g.deg, (double *)g.theta, (double *)g.p, g.st);
+        if (rc) return rc;
+        it0 = 1;
+    } else {
+        TIP_CHECK_CUDA(cudaMemcpyAsync(g.rows, h_rows, (size_t)n_rows * 16, cudaMemcpyHostToDevice, g.st));
+    }
+    for (int it = it0; it < n_iter; ++it) {
         rc = tip_em_step(P, K, g.rows, n_rows, n_rows_r0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
                          g.ws, g.ws_b, flags, g.st);
         if (rc) return rc;

@@ -657,18 +657,26 @@ static int upload_p_const(int K, const double *p, cudaStream_t st, int *slot_out
     return 0;
 }
 
+// phases: 1 = begin (p -> constant bank, clear M_g), 2 = run the fused kernel over `rows`, 4 = end (per-gene
+// finish).  tip_em_step runs all three; the host-buffer entry runs "2" once per row chunk as the chunks arrive.
+constexpr int kPhaseBegin = 1, kPhaseRun = 2, kPhaseEnd = 4, kPhaseAll = 7;
+static int g_phase_slot = 0;
+
 template <int K>
 static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
-                           const double *p, double *stats, double *ws, bool with_ll, bool f32, cudaStream_t st)
+                           const double *p, double *stats, double *ws, bool with_ll, bool f32, int phases,
+                           cudaStream_t st)
 {
-    int slot = 0;
-    {
-        const int rc0 = upload_p_const(K, p, st, &slot, f32);
+    if (phases & kPhaseBegin) {
+        const int rc0 = upload_p_const(K, p, st, &g_phase_slot, f32);
         if (rc0 != 0) return rc0;
+        if (K > 4) TIP_CHECK_CUDA(cudaMemsetAsync(ws, 0, em_tuned_workspace_bytes(P, K), st));
     }
-    if (K > 4) TIP_CHECK_CUDA(cudaMemsetAsync(ws, 0, em_tuned_workspace_bytes(P, K), st));
-    int rc;
-    if (f32) {
+    const int slot = g_phase_slot;
+    int rc = 0;
+    if (!(phases & kPhaseRun) || n_rows == 0) {
+        rc = 0;
+    } else if (f32) {
         rc = launch_variant<K, 1, 16, false, float>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st);
     } else if (with_ll) {
         rc = launch_variant<K, 1, 12, true>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st);
@@ -682,6 +690,7 @@ static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_ro
         }
     }
     if (rc != 0) return rc;
+    if (!(phases & kPhaseEnd)) return 0;
     if constexpr (K > 4) {
         static bool fin_attr = false;
         if (!fin_attr) {
@@ -827,20 +836,21 @@ int launch_loglik_tuned(int K, const int4 *rows, int64_t n_rows, int64_t n_rows_
 }
 
 int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
-                    const double *p, double *stats, double *ws, bool with_ll, bool f32, cudaStream_t st, bool *handled)
+                    const double *p, double *stats, double *ws, bool with_ll, bool f32, cudaStream_t st, bool *handled,
+                    int phases)
 {
     *handled = true;
     switch (K) {
-        case 1: return launch_em_fused<1>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
-        case 2: return launch_em_fused<2>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
-        case 3: return launch_em_fused<3>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
-        case 4: return launch_em_fused<4>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
-        case 5: return launch_em_fused<5>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
-        case 6: return launch_em_fused<6>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
-        case 7: return launch_em_fused<7>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
-        case 8: return launch_em_fused<8>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
-        case 9: return launch_em_fused<9>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
-        case 10: return launch_em_fused<10>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, st);
+        case 1: return launch_em_fused<1>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 2: return launch_em_fused<2>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 3: return launch_em_fused<3>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 4: return launch_em_fused<4>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 5: return launch_em_fused<5>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 6: return launch_em_fused<6>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 7: return launch_em_fused<7>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 8: return launch_em_fused<8>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 9: return launch_em_fused<9>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 10: return launch_em_fused<10>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
         default: *handled = false; return 0;
     }
 }
