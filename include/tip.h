@@ -75,8 +75,8 @@ int tip_pack_rows(const int32_t *d_g1, const int32_t *d_g2, const int32_t *d_g3,
 /* ---- Model.make_iteration, E-step half (TIP.py:987-1012) ----
  * Zeroes d_stats, then accumulates the statistics of `n_rows` packed rows under (d_theta, d_p).
  * n_rows_r0 = rows in the rating-0 block (h_part[0] of tip_pack_rows); both are multiples of 32.
- * d_ws: tip_em_workspace_bytes() bytes of scratch (per-gene M matrices for K = 5..10, per-row s for K > 10;
- *       0 for K <= 4, where it may be NULL). */
+ * d_ws: tip_em_workspace_bytes() bytes of scratch (per-gene M matrices for K = 5..16, per-row s on the any-K
+ *       path; 0 for K <= 4, where it may be NULL). */
 int tip_em_workspace_bytes(int P, int K, int64_t n_rows, unsigned flags, size_t *bytes);
 int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int64_t n_rows_r0, const double *d_theta,
                 const double *d_p, double *d_stats, void *d_ws, size_t ws_bytes, unsigned flags, void *stream);

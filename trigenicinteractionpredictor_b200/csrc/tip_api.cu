@@ -19,6 +19,13 @@ void set_error(const char *fmt, ...)
 }
 
 static bool valid_K(int K) { return K >= 1 && K <= TIP_MAX_K; }
+// K-specialised kernels: K <= 10 always; K = 11..16 in plain fp64 mode (no by-product, no fp32 mode)
+static bool uses_tuned(int K, unsigned flags)
+{
+    if (flags & TIP_EM_FORCE_GENERIC) return false;
+    if (K <= 10) return true;
+    return K <= 16 && !(flags & (TIP_EM_WITH_LOGLIK | TIP_EM_FP32_COMPUTE));
+}
 
 }  // namespace tip
 
@@ -32,8 +39,7 @@ extern "C" int64_t tip_stats_len(int P, int K) { return (int64_t)P * K + 2ll * K
 extern "C" int tip_em_workspace_bytes(int P, int K, int64_t n_rows, unsigned flags, size_t *bytes)
 {
     TIP_REQUIRE(bytes != nullptr && P > 0 && valid_K(K) && n_rows >= 0, "tip_em_workspace_bytes: bad arguments");
-    const bool tuned = !(flags & TIP_EM_FORCE_GENERIC) && K <= 10;
-    *bytes = tuned ? em_tuned_workspace_bytes(P, K) : (size_t)(n_rows < 1 ? 1 : n_rows) * sizeof(double);
+    *bytes = uses_tuned(K, flags) ? em_tuned_workspace_bytes(P, K) : (size_t)(n_rows < 1 ? 1 : n_rows) * sizeof(double);
     return 0;
 }
 
@@ -51,7 +57,7 @@ extern "C" int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int
     TIP_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * (size_t)tip_stats_len(P, K), st));
     if (n_rows == 0) return 0;
     const int4 *rows = reinterpret_cast<const int4 *>(d_rows);
-    if (!(flags & TIP_EM_FORCE_GENERIC) && K <= 10) {
+    if (uses_tuned(K, flags)) {
         const size_t need = em_tuned_workspace_bytes(P, K);
         TIP_REQUIRE(need == 0 || (d_ws != nullptr && ws_bytes >= need),
                     "tip_em_step: K=%d needs %zu bytes of workspace (got %zu), see tip_em_workspace_bytes", K, need, ws_bytes);
@@ -145,7 +151,7 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
     TIP_CHECK_CUDA(cudaMemcpyAsync(g.theta, h_theta, nth, cudaMemcpyHostToDevice, g.st));
     TIP_CHECK_CUDA(cudaMemcpyAsync(g.p, h_p, np, cudaMemcpyHostToDevice, g.st));
     int it0 = 0;
-    const bool tuned = !(flags & TIP_EM_FORCE_GENERIC) && K <= 10;
+    const bool tuned = uses_tuned(K, flags);
     if (tuned && n_iter > 0 && n_rows >= 32 * kHostChunks) {
         // first iteration: rows arrive in chunks on the copy stream, the fused kernel consumes each chunk as
         // soon as it has landed (statistics accumulate across the chunk launches)

@@ -1,4 +1,4 @@
-// K-specialised fused E-step for sm_100a (K = 1..10): the hot kernel of Model.make_iteration
+// K-specialised fused E-step for sm_100a (K = 1..16): the hot kernel of Model.make_iteration
 // (TIP.py:987-1012).  fp64 CUDA-core FMA bound.
 //
 // Persistent single-warp CTAs (12 resident per SM): every control decision depends only on
@@ -37,10 +37,15 @@ namespace tip {
 // 1000 values per link never touch the vector register file or the shared-memory pipe.  Measured on
 // B200 (tools/probes/probe_operand_paths.cu): shared-memory broadcast saturates at 75 % of the DFMA
 // peak whatever the occupancy; the constant path reaches 84 % at 8 warps/SM and 89 % at 20.
-constexpr int kPSlots = 3;           // launches rotate over slots so neighbouring streams do not collide
-constexpr int kPSlotDoubles = 2000;  // max over K<=10 of 2*K*K*KP
-__constant__ double c_pem[kPSlots * kPSlotDoubles];
-__device__ double g_pstage[kPSlots * kPSlotDoubles];
+// Capacity: 63 KB of the 64 KB user constant bank.  K <= 10 needs 2*K*K*KP <= 2000 doubles for both ratings and
+// rotates over three 2000-double slots (so launches on neighbouring streams do not collide); K = 11..14 fits both
+// ratings once; K = 15, 16 fits ONE rating (K*K*KP <= 4096 doubles), so the E-step is launched per rating block.
+constexpr int kPSlots = 3;
+constexpr int kPSlotDoubles = 2000;
+constexpr int kPBankDoubles = 8064;
+constexpr int kMaxTunedK = 16;
+__constant__ double c_pem[kPBankDoubles];
+__device__ double g_pstage[kPBankDoubles];
 
 template <int K, int NBUF>
 struct EmCfg {
@@ -63,15 +68,15 @@ struct EmCfg {
 };
 
 // p[abc][r] (reference layout) -> [r][ab][c padded] staging copy (fp64, or fp32 for the fp32-compute mode),
-// then memcpy to the constant bank
+// then memcpy to the constant bank.  Ratings r_lo .. r_lo + n_r - 1 are staged.
 template <typename T>
-__global__ void stage_p_kernel(int K, int KP, const double *__restrict__ p, T *__restrict__ out)
+__global__ void stage_p_kernel(int K, int KP, int r_lo, int n_r, const double *__restrict__ p, T *__restrict__ out)
 {
-    const int n = 2 * K * K * KP;
+    const int n = n_r * K * K * KP;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const int r = e / (K * K * KP), rem = e - r * (K * K * KP);
         const int pair = rem / KP, c = rem - pair * KP;
-        out[e] = (c < K) ? (T)p[((int64_t)pair * K + c) * 2 + r] : (T)0;
+        out[e] = (c < K) ? (T)p[((int64_t)pair * K + c) * 2 + r_lo + r] : (T)0;
     }
 }
 
@@ -82,14 +87,35 @@ template <int K>
 struct GatherMap {
     static constexpr int UNIT = (K % 2 == 0) ? 2 : 1;
     static constexpr int U = K / UNIT;
-    static constexpr int LPI = 32 / (3 * U);
+    static constexpr int LPI = (3 * U <= 32) ? 32 / (3 * U) : 1;   // links per warp instruction
     static constexpr int ITERS = (32 + LPI - 1) / LPI;
+    static constexpr int UP = (3 * U + 31) / 32;                    // instructions per link when 3U > 32 (odd K >= 11)
 };
 
 template <int K, int RS, int KP>
 __device__ __forceinline__ void gather_tile(const double *__restrict__ theta, const int4 *ids, double *stage, int lane)
 {
     using G = GatherMap<K>;
+    if constexpr (3 * G::U > 32) {
+        // a link's 3U units do not fit one warp instruction: UP instructions per link
+        const int *idw = reinterpret_cast<const int *>(ids);
+#pragma unroll 2
+        for (int l = 0; l < 32; ++l) {
+#pragma unroll
+            for (int j = 0; j < G::UP; ++j) {
+                const int u = lane + 32 * j;
+                if (u < 3 * G::U) {
+                    const int slot = u / G::U, k0 = (u - slot * G::U) * G::UNIT;
+                    const int g = idw[l * 4 + slot];
+                    if (G::UNIT == 2)
+                        cp_async_16(stage + l * RS + slot * KP + k0, theta + (int64_t)g * K + k0);
+                    else
+                        cp_async_8(stage + l * RS + slot * KP + k0, theta + (int64_t)g * K + k0);
+                }
+            }
+        }
+        return;
+    }
     const int sub = lane / (3 * G::U), rem = lane - sub * (3 * G::U);
     const int slot = rem / G::U, k0 = (rem - slot * G::U) * G::UNIT;
     const bool active = sub < G::LPI;
@@ -151,7 +177,7 @@ struct ScatterMap {
 template <int K, int NBUF, int MINB, bool LL, typename T>
 __global__ void __launch_bounds__(32, MINB)
     em_fused_kernel(int P, const int4 *__restrict__ rows, int n_tiles, int n_tiles_r0, const double *__restrict__ theta,
-                    int p_slot, double *__restrict__ stats, double *__restrict__ Mg, int dbg)
+                    int p_off0, int p_off1, double *__restrict__ stats, double *__restrict__ Mg, int dbg)
 {
     using C = EmCfg<K, NBUF>;
     constexpr int KP = C::KP, RS = C::RS, K3 = C::K3, CB = C::CB, RC = C::RC, CA = C::CA;
@@ -283,8 +309,8 @@ __global__ void __launch_bounds__(32, MINB)
             if constexpr (K % 2 == 0) bulk_wait_read();  // the previous tile's bulk reductions have read cbuf
             double *row = stage + lane * RS;
             double *crow = cbuf + lane * RC;
-            // p index in units of T inside this launch's constant-bank slot
-            const int pbase = p_slot * (kPSlotDoubles * (int)(sizeof(double) / sizeof(T))) + r * (K * K * KP);
+            // p index (units of T) of this tile's rating inside the constant bank
+            const int pbase = r ? p_off1 : p_off0;
             const T *cp = reinterpret_cast<const T *>(c_pem);
             T tb[KP], tc[KP], v[K], w[KP];
 #pragma unroll
@@ -487,7 +513,15 @@ __global__ void __launch_bounds__(32, MINB)
 // ---------------------------------------------------------------------------------------------
 constexpr int kFinThreads = 256;
 constexpr int kFinWarps = kFinThreads / 32;
-constexpr int kFinChunk = 48;  // genes staged in shared memory per pass (both ratings)
+// genes staged in shared memory per pass (both ratings): as many as fit beside p in ~200 KB, at most 48
+template <int K>
+constexpr int fin_chunk()
+{
+    const long avail = 200 * 1024 - 16L * K * K * K;
+    const long per_gene = 16L * K * K + 8L * K;
+    const long n = avail / per_gene;
+    return n > 48 ? 48 : (n < 1 ? 1 : (int)n);
+}
 
 template <int K>
 __global__ void __launch_bounds__(kFinThreads)
@@ -497,6 +531,7 @@ __global__ void __launch_bounds__(kFinThreads)
     constexpr int KK = K * K, K3 = K * K * K;
     constexpr int CPT = (K3 + kFinThreads - 1) / kFinThreads;  // S cells per thread
     constexpr int BPL = (KK + 31) / 32;                        // (b,c) pairs per lane
+    constexpr int kFinChunk = fin_chunk<K>();
     extern __shared__ __align__(16) double fsm[];
     double *sP = fsm;                         // [2][K3]   p[r][a][bc]
     double *sT = sP + 2 * K3;                 // [kFinChunk][K]
@@ -573,7 +608,7 @@ __global__ void __launch_bounds__(kFinThreads)
 template <int K>
 constexpr size_t fin_smem_bytes()
 {
-    return sizeof(double) * (2 * K * K * K + kFinChunk * K + 2 * kFinChunk * K * K);
+    return sizeof(double) * (2 * K * K * K + fin_chunk<K>() * K + 2 * fin_chunk<K>() * K * K);
 }
 
 static int g_slot_counter = 0;
@@ -605,8 +640,8 @@ static int em_debug()
 }
 
 template <int K, int NBUF, int MINB, bool LL, typename T = double>
-static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, int slot,
-                          double *stats, double *Mg, cudaStream_t st)
+static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, int p_off0,
+                          int p_off1, double *stats, double *Mg, cudaStream_t st)
 {
     using C = EmCfg<K, NBUF>;
     static int blocks_per_sm = 0;
@@ -625,68 +660,108 @@ static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_row
     int64_t cap = (int64_t)sm_count() * blocks_per_sm;
     int grid = (int)(n_tiles < cap ? n_tiles : cap);
     if (grid < 1) grid = 1;
-    em_fused_kernel<K, NBUF, MINB, LL, T><<<grid, 32, C::SMEM, st>>>(P, rows, (int)n_tiles, (int)(n_rows_r0 / 32), theta, slot,
-                                                                 stats, Mg, em_debug());
+    em_fused_kernel<K, NBUF, MINB, LL, T><<<grid, 32, C::SMEM, st>>>(P, rows, (int)n_tiles, (int)(n_rows_r0 / 32), theta, p_off0,
+                                                                 p_off1, stats, Mg, em_debug());
     TIP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 size_t em_tuned_workspace_bytes(int P, int K)
 {
-    if (K <= 4 || K > 10) return 0;
+    if (K <= 4 || K > kMaxTunedK) return 0;
     return sizeof(double) * 2 * (size_t)P * K * K;  // M_g[r][gene][b][c]
 }
 
-// p -> E-step layout -> constant bank slot (stream-ordered); returns the slot in *slot_out
-static int upload_p_const(int K, const double *p, cudaStream_t st, int *slot_out, bool f32 = false)
+// ratings [r_lo, r_lo + n_r) of p -> E-step layout -> constant bank at double-offset base_d (stream-ordered)
+static int upload_p_const(int K, const double *p, int r_lo, int n_r, int base_d, bool f32, cudaStream_t st)
 {
     const int KP = K + (K & 1);
     static double *stage_ptr = nullptr;
     if (!stage_ptr) TIP_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void **>(&stage_ptr), g_pstage));
-    const int slot = (g_slot_counter++) % kPSlots;
-    const int n = 2 * K * K * KP;
-    double *dst = stage_ptr + slot * kPSlotDoubles;
+    const int n = n_r * K * K * KP;
+    double *dst = stage_ptr + base_d;
     if (f32)
-        stage_p_kernel<float><<<(n + 255) / 256, 256, 0, st>>>(K, KP, p, reinterpret_cast<float *>(dst));
+        stage_p_kernel<float><<<(n + 255) / 256, 256, 0, st>>>(K, KP, r_lo, n_r, p, reinterpret_cast<float *>(dst));
     else
-        stage_p_kernel<double><<<(n + 255) / 256, 256, 0, st>>>(K, KP, p, dst);
+        stage_p_kernel<double><<<(n + 255) / 256, 256, 0, st>>>(K, KP, r_lo, n_r, p, dst);
     TIP_CHECK_CUDA(cudaGetLastError());
-    TIP_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_pem, dst, (f32 ? sizeof(float) : sizeof(double)) * n,
-                                           sizeof(double) * slot * kPSlotDoubles, cudaMemcpyDeviceToDevice, st));
-    *slot_out = slot;
+    TIP_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_pem, dst, (f32 ? sizeof(float) : sizeof(double)) * n, sizeof(double) * base_d,
+                                           cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+// both ratings of a K <= 10 table into the next rotating slot; returns the slot's double-offset
+static int upload_p_slot(int K, const double *p, bool f32, cudaStream_t st, int *base_d)
+{
+    *base_d = ((g_slot_counter++) % kPSlots) * kPSlotDoubles;
+    return upload_p_const(K, p, 0, 2, *base_d, f32, st);
 }
 
 // phases: 1 = begin (p -> constant bank, clear M_g), 2 = run the fused kernel over `rows`, 4 = end (per-gene
 // finish).  tip_em_step runs all three; the host-buffer entry runs "2" once per row chunk as the chunks arrive.
-constexpr int kPhaseBegin = 1, kPhaseRun = 2, kPhaseEnd = 4, kPhaseAll = 7;
-static int g_phase_slot = 0;
+constexpr int kPhaseBegin = 1, kPhaseRun = 2, kPhaseEnd = 4;
+static int g_phase_off0 = 0, g_phase_off1 = 0;
+
+template <int K, int NBUF, int MINB, bool LL, typename T>
+static int run_rows(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
+                    double *stats, double *ws, cudaStream_t st)
+{
+    constexpr int KP = K + (K & 1), TBL = K * K * KP;
+    if constexpr (2 * TBL <= kPBankDoubles) {
+        return launch_variant<K, NBUF, MINB, LL, T>(P, rows, n_rows, n_rows_r0, theta, g_phase_off0, g_phase_off1, stats,
+                                                    ws, st);
+    } else {
+        // one rating fits the bank at a time: upload p_r, run that rating block, in stream order
+        for (int r = 0; r < 2; ++r) {
+            const int64_t lo = r == 0 ? 0 : n_rows_r0, hi = r == 0 ? n_rows_r0 : n_rows;
+            if (hi <= lo) continue;
+            int rc = upload_p_const(K, p, r, 1, 0, sizeof(T) == 4, st);
+            if (rc != 0) return rc;
+            rc = launch_variant<K, NBUF, MINB, LL, T>(P, rows + lo, hi - lo, r == 0 ? hi - lo : 0, theta, 0, 0, stats, ws, st);
+            if (rc != 0) return rc;
+        }
+        return 0;
+    }
+}
 
 template <int K>
 static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
                            const double *p, double *stats, double *ws, bool with_ll, bool f32, int phases,
                            cudaStream_t st)
 {
+    constexpr int KP = K + (K & 1), TBL = K * K * KP;
+    const int tscale = f32 ? 2 : 1;  // offsets are in units of T
     if (phases & kPhaseBegin) {
-        const int rc0 = upload_p_const(K, p, st, &g_phase_slot, f32);
-        if (rc0 != 0) return rc0;
+        if constexpr (2 * TBL <= kPSlotDoubles) {
+            int base = 0;
+            const int rc0 = upload_p_slot(K, p, f32, st, &base);
+            if (rc0 != 0) return rc0;
+            g_phase_off0 = base * tscale;
+            g_phase_off1 = base * tscale + TBL;
+        } else if constexpr (2 * TBL <= kPBankDoubles) {
+            const int rc0 = upload_p_const(K, p, 0, 2, 0, f32, st);
+            if (rc0 != 0) return rc0;
+            g_phase_off0 = 0;
+            g_phase_off1 = TBL;
+        }
         if (K > 4) TIP_CHECK_CUDA(cudaMemsetAsync(ws, 0, em_tuned_workspace_bytes(P, K), st));
     }
-    const int slot = g_phase_slot;
     int rc = 0;
     if (!(phases & kPhaseRun) || n_rows == 0) {
         rc = 0;
+    } else if constexpr (K > 10) {
+        rc = run_rows<K, 1, 12, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st);
     } else if (f32) {
-        rc = launch_variant<K, 1, 16, false, float>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st);
+        rc = run_rows<K, 1, 16, false, float>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st);
     } else if (with_ll) {
-        rc = launch_variant<K, 1, 12, true>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st);
+        rc = run_rows<K, 1, 12, true, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st);
     } else {
         switch (em_variant()) {
-            case 1: rc = launch_variant<K, 2, 8, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
-            case 2: rc = launch_variant<K, 2, 12, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
-            case 3: rc = launch_variant<K, 1, 16, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
-            case 4: rc = launch_variant<K, 1, 14, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
-            default: rc = launch_variant<K, 1, 12, false>(P, rows, n_rows, n_rows_r0, theta, slot, stats, ws, st); break;
+            case 1: rc = run_rows<K, 2, 8, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
+            case 2: rc = run_rows<K, 2, 12, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
+            case 3: rc = run_rows<K, 1, 16, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
+            case 4: rc = run_rows<K, 1, 14, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
+            default: rc = run_rows<K, 1, 12, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
         }
     }
     if (rc != 0) return rc;
@@ -795,11 +870,12 @@ template <int K>
 static int launch_loglik_fused(const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
                                double *out, double *partials, unsigned *counter, int max_blocks, cudaStream_t st)
 {
-    int slot = 0;
+    int base = 0;
     {
-        const int rc0 = upload_p_const(K, p, st, &slot);
+        const int rc0 = upload_p_slot(K, p, false, st, &base);
         if (rc0 != 0) return rc0;
     }
+    const int slot = base / kPSlotDoubles;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         int nb = 0;
@@ -851,6 +927,12 @@ int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_ro
         case 8: return launch_em_fused<8>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
         case 9: return launch_em_fused<9>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
         case 10: return launch_em_fused<10>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 11: return launch_em_fused<11>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 12: return launch_em_fused<12>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 13: return launch_em_fused<13>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 14: return launch_em_fused<14>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 15: return launch_em_fused<15>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 16: return launch_em_fused<16>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
         default: *handled = false; return 0;
     }
 }
