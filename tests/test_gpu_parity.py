@@ -325,3 +325,23 @@ def test_full_size_properties_cfg2(torch_cuda):
         assert eng.loglik("train") > ll0                                 # EM ascent
         outs.append((th, p))
     assert _relerr(outs[0][0], outs[1][0]) < 1e-10 and _relerr(outs[0][1], outs[1][1]) < 1e-10
+
+
+def test_cli_writes_reference_shaped_sample_files(torch_cuda, tmp_path, capsys):
+    """The command line of TIP.py:1148-1279: same flags, Sample_{s}_K{k}.csv naming, skip-if-exists."""
+    from trigenicinteractionpredictor_b200 import main
+    out = str(tmp_path) + os.sep
+    argv = ["-t", os.path.join(BASE, "train1.dat"), "-e", os.path.join(BASE, "test1.dat"), "-k", "2", "-i", "300",
+            "-f", "5", "-b", "10", "-n", "2", "-o", out, "--seed", "1000"]
+    assert main(argv) == 0
+    files = sorted(os.listdir(out))
+    assert files == ["Sample_0_K2.csv", "Sample_1_K2.csv"]
+    got = open(os.path.join(out, "Sample_0_K2.csv"), encoding="utf-8").read().split("\n")
+    exp = open(os.path.join(BASE, "Sample_0_K2.csv"), encoding="utf-8").read().split("\n")
+    assert got[0].split("\t")[0] == "Max Likelihood:" and len(got) == len(exp)
+    assert float(got[0].split("\t")[1]) == pytest.approx(float(exp[0].split("\t")[1]), rel=1e-9)
+    assert got[2:8] == exp[2:8]                      # P, #links, K, R lines are identical text
+    stamp = os.path.getmtime(os.path.join(out, "Sample_0_K2.csv"))
+    assert main(argv) == 0                           # second run: both samples exist and are skipped
+    assert os.path.getmtime(os.path.join(out, "Sample_0_K2.csv")) == stamp
+    assert "Likelihood has converged" in capsys.readouterr().out

@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""BASELINE config 5: K sweep at 10M triplets on one B200 (E-step + M-step time per iteration)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from trigenicinteractionpredictor_b200 import synth  # noqa: E402
+from trigenicinteractionpredictor_b200.engine import EMEngine  # noqa: E402
+
+L = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+Ks = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [2, 3, 4, 6, 8, 10, 12, 16, 20, 24, 32]
+P = 6000
+dev = torch.device("cuda:0")
+g1, g2, g3, lab = synth.planted_links_soa(P, L, seed=7, device=dev)
+g1[:P] = torch.arange(P, dtype=torch.int32, device=dev)
+out = []
+for K in Ks:
+    eng = EMEngine(P, K, device=dev)
+    eng.set_train_links(g1, g2, g3, 1 - lab, lab)
+    rng = np.random.default_rng(K)
+    theta = rng.dirichlet(np.ones(K), size=P)
+    pr = rng.random((K, K, K, 2))
+    pr /= pr.sum(axis=3, keepdims=True)
+    eng.set_params(theta, pr)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.em_iteration()
+    torch.cuda.synchronize()
+    n = 5 if K <= 16 else 2
+    a.record()
+    for _ in range(n):
+        eng.em_iteration()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / n
+    rec = {"K": K, "links": L, "ms_per_iteration": ms, "link_updates_per_s": L / ms * 1e3,
+           "algorithmic_tflops": 6.0 * K ** 3 * L / ms * 1e3 / 1e12, "kernel": "specialised" if K <= 16 else "any-K"}
+    out.append(rec)
+    print(json.dumps(rec), flush=True)
+    del eng
+    torch.cuda.empty_cache()
