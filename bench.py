@@ -331,6 +331,27 @@ def run_ours(args):
         line["value_fp32_compute"] = L_total / (t32 / args.steps * 1e-3)
         line["fp32_compute_roofline_frac"] = (6.0 * K ** 3 * L_local / (t32 / args.steps * 1e-3) / 1e12) / peak32 if rank == 0 else None
         del eng32
+        # ---- gene-segmented mode (TIP_EM_GENE_SEGMENTED): 2K^2 instead of 2K^3 FMA per link; not FMA bound ----
+        engs = EMEngine(P, K, device=dev, flags=_cabi.TIP_EM_GENE_SEGMENTED)
+        engs.set_train_links(*_links_again(synth, P, L_local, rank, dev))
+        engs.set_params(theta0, pr0)
+        engs.capture_graphs()
+        for _ in range(3):
+            flush_l2()
+            engs.graph_step()
+        ts = 0.0
+        for _ in range(args.steps):
+            flush_l2()
+            a.record()
+            engs.graph_step()
+            b.record()
+            torch.cuda.synchronize(dev)
+            ts += a.elapsed_time(b)
+        line["value_gene_segmented"] = L_total / (ts / args.steps * 1e-3)
+        line["gene_segmented_note"] = ("same statistics to rounding with 2K^2+K^2 FMA per link (+2K^3 per gene and rating); "
+                                       "bound by the theta gather and the fp64 reductions, so it is reported beside, not as, "
+                                       "the FMA-roofline kernel")
+        del engs
 
     # ---- end to end through host buffers ----
     e2e = _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist)
@@ -357,6 +378,13 @@ def run_ours(args):
         sys.stderr.flush()
         os._exit(0)
     return 0
+
+
+def _links_again(synth, P, L_local, rank, dev):
+    import torch
+    g1, g2, g3, lab = synth.planted_links_soa(P, L_local, seed=100 + rank, device=dev)
+    g1[:P] = torch.arange(P, dtype=torch.int32, device=dev)
+    return g1, g2, g3, 1 - lab, lab
 
 
 def _measure_peak(lib, kind):

@@ -117,6 +117,36 @@ def test_fp32_compute_mode_within_1e5(torch_cuda, K):
     assert m.calculate_metrics()[3] == pytest.approx(tr["metrics"][3], abs=1e-6)
 
 
+@pytest.mark.parametrize("K", [5, 8, 9, 10, 13, 16])
+def test_gene_segmented_mode_matches_oracle(torch_cuda, K):
+    """TIP_EM_GENE_SEGMENTED (flag 8): p contracted with theta per gene first - same statistics to rounding."""
+    from oracle import mmsbm_oracle as orc
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    P, L = 300, 6000 if K <= 10 else 1500
+    g, n0, n1, theta, pr = _random_problem(P, L, K, 40 + K)
+    cnt = np.stack([n0, n1], axis=1).astype(np.int64)
+    ent, enp, deg = orc.em_step_np(theta, pr, g.astype(np.int64), cnt, return_stats=True)
+    th1, pr1 = orc.normalise_np(ent, enp, deg)
+    eng = EMEngine(P, K, flags=8)
+    eng.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+    eng.set_params(theta, pr)
+    eng.em_iteration()
+    th, p = eng.get_params()
+    assert _relerr(th, th1) < 1e-11 and _relerr(p, pr1) < 1e-11
+
+
+def test_gene_segmented_mode_reference_trace(torch_cuda):
+    tr = np.load(os.path.join(BASE, "trace_K10.npz"))
+    m = _model(BASE, "train1.dat", "test1.dat", flags=8)
+    random.seed(1000)
+    m.initialize_parameters(10)
+    for it in range(5):
+        m.make_iteration()
+        assert _relerr(m.theta, tr["theta%d" % (it + 1)]) < RTOL
+        assert _relerr(m.pr, tr["pr%d" % (it + 1)]) < RTOL
+        assert m.compute_likelihood() == pytest.approx(tr["loglik"][it + 1], rel=RTOL)
+
+
 def test_fp32_mode_is_rejected_where_it_does_not_exist(torch_cuda):
     from trigenicinteractionpredictor_b200._cabi import TipLibraryError
     from trigenicinteractionpredictor_b200.engine import EMEngine

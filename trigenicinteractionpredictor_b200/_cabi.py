@@ -20,6 +20,7 @@ TIP_EM_DEFAULT = 0
 TIP_EM_FORCE_GENERIC = 1
 TIP_EM_FP32_COMPUTE = 2
 TIP_EM_WITH_LOGLIK = 4
+TIP_EM_GENE_SEGMENTED = 8
 
 # name -> (restype, argtypes); must list every function include/tip.h declares (tests check this)
 SIGNATURES = {

@@ -26,6 +26,7 @@ static bool uses_tuned(int K, unsigned flags)
     if (K <= 10) return true;
     return K <= 16 && !(flags & (TIP_EM_WITH_LOGLIK | TIP_EM_FP32_COMPUTE));
 }
+static bool seg_flag(unsigned flags) { return (flags & TIP_EM_GENE_SEGMENTED) != 0; }
 
 }  // namespace tip
 
@@ -39,7 +40,8 @@ extern "C" int64_t tip_stats_len(int P, int K) { return (int64_t)P * K + 2ll * K
 extern "C" int tip_em_workspace_bytes(int P, int K, int64_t n_rows, unsigned flags, size_t *bytes)
 {
     TIP_REQUIRE(bytes != nullptr && P > 0 && valid_K(K) && n_rows >= 0, "tip_em_workspace_bytes: bad arguments");
-    *bytes = uses_tuned(K, flags) ? em_tuned_workspace_bytes(P, K) : (size_t)(n_rows < 1 ? 1 : n_rows) * sizeof(double);
+    *bytes = uses_tuned(K, flags) ? em_tuned_workspace_bytes(P, K, seg_flag(flags))
+                                  : (size_t)(n_rows < 1 ? 1 : n_rows) * sizeof(double);
     return 0;
 }
 
@@ -54,16 +56,19 @@ extern "C" int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int
     TIP_REQUIRE(d_theta && d_p && d_stats && (d_rows || n_rows == 0), "tip_em_step: null pointer");
     TIP_REQUIRE(!(flags & TIP_EM_FP32_COMPUTE) || (K <= 10 && !(flags & (TIP_EM_FORCE_GENERIC | TIP_EM_WITH_LOGLIK))),
                 "tip_em_step: TIP_EM_FP32_COMPUTE exists for the K <= 10 kernels only, without FORCE_GENERIC / WITH_LOGLIK");
+    TIP_REQUIRE(!seg_flag(flags) || (K <= 16 && !(flags & (TIP_EM_FORCE_GENERIC | TIP_EM_WITH_LOGLIK | TIP_EM_FP32_COMPUTE))),
+                "tip_em_step: TIP_EM_GENE_SEGMENTED exists for the K <= 16 fp64 kernels only, without other mode flags");
     TIP_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * (size_t)tip_stats_len(P, K), st));
     if (n_rows == 0) return 0;
     const int4 *rows = reinterpret_cast<const int4 *>(d_rows);
     if (uses_tuned(K, flags)) {
-        const size_t need = em_tuned_workspace_bytes(P, K);
+        const size_t need = em_tuned_workspace_bytes(P, K, seg_flag(flags));
         TIP_REQUIRE(need == 0 || (d_ws != nullptr && ws_bytes >= need),
                     "tip_em_step: K=%d needs %zu bytes of workspace (got %zu), see tip_em_workspace_bytes", K, need, ws_bytes);
         bool handled = false;
         int rc = launch_em_tuned(P, K, rows, n_rows, n_rows_r0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws),
-                                 (flags & TIP_EM_WITH_LOGLIK) != 0, (flags & TIP_EM_FP32_COMPUTE) != 0, st, &handled);
+                                 (flags & TIP_EM_WITH_LOGLIK) != 0, (flags & TIP_EM_FP32_COMPUTE) != 0, seg_flag(flags), st,
+                                 &handled);
         if (rc != 0 || handled) return rc;
     }
     TIP_REQUIRE(d_ws != nullptr && ws_bytes >= (size_t)n_rows * sizeof(double),
@@ -156,11 +161,11 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
         // first iteration: rows arrive in chunks on the copy stream, the fused kernel consumes each chunk as
         // soon as it has landed (statistics accumulate across the chunk launches)
         const int4 *rows = reinterpret_cast<const int4 *>(g.rows);
-        const bool ll = (flags & TIP_EM_WITH_LOGLIK) != 0, f32 = (flags & TIP_EM_FP32_COMPUTE) != 0;
+        const bool ll = (flags & TIP_EM_WITH_LOGLIK) != 0, f32 = (flags & TIP_EM_FP32_COMPUTE) != 0, sg = seg_flag(flags);
         bool handled = false;
         TIP_CHECK_CUDA(cudaMemsetAsync(g.stats, 0, nst, g.st));
         rc = launch_em_tuned(P, K, rows, 0, 0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
-                             (double *)g.ws, ll, f32, g.st, &handled, 1);
+                             (double *)g.ws, ll, f32, sg, g.st, &handled, 1);
         if (rc) return rc;
         const int64_t n_tiles = n_rows / 32, per = (n_tiles + kHostChunks - 1) / kHostChunks;
         for (int c = 0; c < kHostChunks; ++c) {
@@ -173,11 +178,11 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
             int64_t r0 = n_rows_r0 / 32 - t0;
             r0 = r0 < 0 ? 0 : (r0 > t1 - t0 ? t1 - t0 : r0);
             rc = launch_em_tuned(P, K, rows + t0 * 32, (t1 - t0) * 32, r0 * 32, (const double *)g.theta, (const double *)g.p,
-                                 (double *)g.stats, (double *)g.ws, ll, f32, g.st, &handled, 2);
+                                 (double *)g.stats, (double *)g.ws, ll, f32, sg, g.st, &handled, 2);
             if (rc) return rc;
         }
         rc = launch_em_tuned(P, K, rows, 0, 0, (const double *)g.theta, (const double *)g.p, (double *)g.stats, (double *)g.ws,
-                             ll, f32, g.st, &handled, 4);
+                             ll, f32, sg, g.st, &handled, 4);
         if (rc) return rc;
         rc = tip_normalise(P, K, (const double *)g.stats, (const int32_t *)g.deg, (double *)g.theta, (double *)g.p, g.st);
         if (rc) return rc;

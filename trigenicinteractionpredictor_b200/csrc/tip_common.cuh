@@ -84,9 +84,9 @@ __host__ __device__ inline int64_t stats_off_ll(int P, int K) { return (int64_t)
 int launch_em_generic(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
                       const double *p, double *stats, double *s_ws, cudaStream_t st);
 int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
-                    const double *p, double *stats, double *ws, bool with_ll, bool f32, cudaStream_t st, bool *handled,
-                    int phases = 7);
-size_t em_tuned_workspace_bytes(int P, int K);
+                    const double *p, double *stats, double *ws, bool with_ll, bool f32, bool seg, cudaStream_t st,
+                    bool *handled, int phases = 7);
+size_t em_tuned_workspace_bytes(int P, int K, bool seg);
 int launch_loglik(int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
                   double *out, void *ws, bool force_generic, cudaStream_t st);
 int launch_loglik_tuned(int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,

@@ -174,10 +174,18 @@ struct ScatterMap {
 // T = double: the fp64 path (1e-9 parity).  T = float: fp32-compute / fp64-accumulate mode (TIP_EM_FP32_COMPUTE):
 // only the two K^3 contractions of phase A run in fp32 (FFMA, p as fp32 in the constant bank); the normaliser,
 // s, every contribution that leaves the thread, M_g and all statistics stay fp64 (1e-5 parity).
-template <int K, int NBUF, int MINB, bool LL, typename T>
+//
+// SEG = true (TIP_EM_GENE_SEGMENTED, K >= 5): the gene-segmented factorisation applied to phase A as well.  p is
+// contracted with th_a once per (gene, rating) by seg_prep_kernel, Z_g[b][c] = sum_a th_g[a] p[abc], and a link then
+// costs 2 K^2 DFMA instead of 2 K^3:   y[b] = sum_c Z_g[b][c] th_c[c],   w[c] = sum_b th_b[b] Z_g[b][c],
+// d = eps + sum_b th_b[b] y[b].  Lanes read Z of their own slot-a gene through L1 (one address per run of equal
+// gene, so a warp instruction touches one or two lines).  The kernel is then bound by the theta gather and the
+// slot-b/c reductions, not by the FMA pipe; bench.py reports it separately from the headline kernel.
+template <int K, int NBUF, int MINB, bool LL, typename T, bool SEG>
 __global__ void __launch_bounds__(32, MINB)
     em_fused_kernel(int P, const int4 *__restrict__ rows, int n_tiles, int n_tiles_r0, const double *__restrict__ theta,
-                    int p_off0, int p_off1, double *__restrict__ stats, double *__restrict__ Mg, int dbg)
+                    int p_off0, int p_off1, double *__restrict__ stats, double *__restrict__ Mg,
+                    const double *__restrict__ Zg, int dbg)
 {
     using C = EmCfg<K, NBUF>;
     constexpr int KP = C::KP, RS = C::RS, K3 = C::K3, CB = C::CB, RC = C::RC, CA = C::CA;
@@ -324,12 +332,41 @@ __global__ void __launch_bounds__(32, MINB)
 #pragma unroll
             for (int k = 0; k < K; ++k) v[k] = (T)0;
             T dsum = (T)0;
+            if constexpr (SEG) {
+                // per-lane pointer to Z of this link's slot-a gene and rating
+                const double *Zrow = Zg + ((int64_t)r_v * P + me.x) * (K * K);
+#pragma unroll
+                for (int b = 0; b < K; ++b) {
+                    T y0 = (T)0, y1 = (T)0;
+#pragma unroll
+                    for (int c = 0; c < K; c += 2) {
+                        if constexpr (K % 2 == 0) {
+                            const double2 z = __ldg(reinterpret_cast<const double2 *>(Zrow + b * K + c));
+                            y0 = fma((T)z.x, tc[c], y0);
+                            w[c] = fma(tb[b], (T)z.x, w[c]);
+                            y1 = fma((T)z.y, tc[c + 1], y1);
+                            w[c + 1] = fma(tb[b], (T)z.y, w[c + 1]);
+                        } else {
+                            const T z0 = (T)__ldg(Zrow + b * K + c);
+                            y0 = fma(z0, tc[c], y0);
+                            w[c] = fma(tb[b], z0, w[c]);
+                            if (c + 1 < K) {
+                                const T z1 = (T)__ldg(Zrow + b * K + c + 1);
+                                y1 = fma(z1, tc[c + 1], y1);
+                                w[c + 1] = fma(tb[b], z1, w[c + 1]);
+                            }
+                        }
+                    }
+                    v[b] = y0 + y1;
+                    dsum = fma(tb[b], v[b], dsum);
+                }
+            }
             const double *ta_p = row;  // walked separately so that `a` only ever indexes the constant bank
             double *tt_p = crow;
             // (A per-lane ld.const prefetch of the next a-slice was tried against the 88 % constant-cache hit rate
             // ncu reports: the divergent constant access serialises and costs 35 % - not kept.)
 #pragma unroll 1
-            for (int a = 0; a < K; ++a) {
+            for (int a = 0; a < (SEG ? 0 : K); ++a) {
                 const T ta = (T)(*ta_p++);
                 const int pa = pbase + a * (K * KP);
                 T u = (T)0;
@@ -505,6 +542,22 @@ __global__ void __launch_bounds__(32, MINB)
     }
 }
 
+// Z[r][g][bc] = sum_a theta[g][a] * p[a][bc][r]   (TIP_EM_GENE_SEGMENTED; 2*P*K^3 FMA per iteration in total)
+__global__ void seg_prep_kernel(int P, int K, const double *__restrict__ theta, const double *__restrict__ p,
+                                double *__restrict__ Zg)
+{
+    const int KK = K * K;
+    const int64_t n = 2ll * P * KK;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / ((int64_t)P * KK));
+        const int64_t rem = e - (int64_t)r * P * KK;
+        const int g = (int)(rem / KK), bc = (int)(rem - (int64_t)g * KK);
+        double z = 0.0;
+        for (int a = 0; a < K; ++a) z = fma(__ldg(theta + (int64_t)g * K + a), __ldg(p + ((int64_t)a * KK + bc) * 2 + r), z);
+        Zg[e] = z;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Per-gene finish of the gene-segmented factorisation (K >= 5), once per iteration:
 //   Ntheta[g][a] += th_g[a] * sum_r sum_bc p[a][b][c][r] M_{r,g}[b][c]
@@ -639,19 +692,19 @@ static int em_debug()
     return v;
 }
 
-template <int K, int NBUF, int MINB, bool LL, typename T = double>
+template <int K, int NBUF, int MINB, bool LL, typename T = double, bool SEG = false>
 static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, int p_off0,
                           int p_off1, double *stats, double *Mg, cudaStream_t st)
 {
     using C = EmCfg<K, NBUF>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL, T, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)C::SMEM));
-        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL, T>,
+        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL, T, SEG>,
                                             cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int nb = 0;
-        TIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, em_fused_kernel<K, NBUF, MINB, LL, T>, 32, C::SMEM));
+        TIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, em_fused_kernel<K, NBUF, MINB, LL, T, SEG>, 32, C::SMEM));
         TIP_REQUIRE(nb >= 1, "em_fused_kernel<%d> does not fit on an SM (smem %zu)", K, C::SMEM);
         blocks_per_sm = nb;
     }
@@ -660,16 +713,18 @@ static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_row
     int64_t cap = (int64_t)sm_count() * blocks_per_sm;
     int grid = (int)(n_tiles < cap ? n_tiles : cap);
     if (grid < 1) grid = 1;
-    em_fused_kernel<K, NBUF, MINB, LL, T><<<grid, 32, C::SMEM, st>>>(P, rows, (int)n_tiles, (int)(n_rows_r0 / 32), theta, p_off0,
-                                                                 p_off1, stats, Mg, em_debug());
+    em_fused_kernel<K, NBUF, MINB, LL, T, SEG><<<grid, 32, C::SMEM, st>>>(
+        P, rows, (int)n_tiles, (int)(n_rows_r0 / 32), theta, p_off0, p_off1, stats, Mg,
+        SEG ? Mg + 2 * (size_t)P * K * K : nullptr, em_debug());
     TIP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-size_t em_tuned_workspace_bytes(int P, int K)
+size_t em_tuned_workspace_bytes(int P, int K, bool seg)
 {
     if (K <= 4 || K > kMaxTunedK) return 0;
-    return sizeof(double) * 2 * (size_t)P * K * K;  // M_g[r][gene][b][c]
+    // M_g[r][gene][b][c], followed by Z_g[r][gene][b][c] in the gene-segmented mode
+    return sizeof(double) * 2 * (size_t)P * K * K * (seg ? 2 : 1);
 }
 
 // ratings [r_lo, r_lo + n_r) of p -> E-step layout -> constant bank at double-offset base_d (stream-ordered)
@@ -726,13 +781,22 @@ static int run_rows(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, 
 
 template <int K>
 static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
-                           const double *p, double *stats, double *ws, bool with_ll, bool f32, int phases,
+                           const double *p, double *stats, double *ws, bool with_ll, bool f32, bool seg, int phases,
                            cudaStream_t st)
 {
     constexpr int KP = K + (K & 1), TBL = K * K * KP;
     const int tscale = f32 ? 2 : 1;  // offsets are in units of T
+    if (K <= 4) seg = false;         // thread-private S path: nothing to segment
     if (phases & kPhaseBegin) {
-        if constexpr (2 * TBL <= kPSlotDoubles) {
+        if (seg) {
+            // Z_g = theta_g . p  for every (gene, rating), into the second half of the workspace
+            const int64_t n = 2ll * P * K * K;
+            const int threads = 256;
+            int64_t want = (n + threads - 1) / threads;
+            const int grid = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
+            seg_prep_kernel<<<grid, threads, 0, st>>>(P, K, theta, p, ws + 2 * (size_t)P * K * K);
+            TIP_CHECK_CUDA(cudaGetLastError());
+        } else if constexpr (2 * TBL <= kPSlotDoubles) {
             int base = 0;
             const int rc0 = upload_p_slot(K, p, f32, st, &base);
             if (rc0 != 0) return rc0;
@@ -744,11 +808,14 @@ static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_ro
             g_phase_off0 = 0;
             g_phase_off1 = TBL;
         }
-        if (K > 4) TIP_CHECK_CUDA(cudaMemsetAsync(ws, 0, em_tuned_workspace_bytes(P, K), st));
+        if (K > 4) TIP_CHECK_CUDA(cudaMemsetAsync(ws, 0, em_tuned_workspace_bytes(P, K, false), st));  // M_g only
     }
     int rc = 0;
     if (!(phases & kPhaseRun) || n_rows == 0) {
         rc = 0;
+    } else if (seg) {
+        if constexpr (K > 4)
+            rc = launch_variant<K, 1, 16, false, double, true>(P, rows, n_rows, n_rows_r0, theta, 0, 0, stats, ws, st);
     } else if constexpr (K > 10) {
         rc = run_rows<K, 1, 12, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st);
     } else if (f32) {
@@ -912,27 +979,27 @@ int launch_loglik_tuned(int K, const int4 *rows, int64_t n_rows, int64_t n_rows_
 }
 
 int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
-                    const double *p, double *stats, double *ws, bool with_ll, bool f32, cudaStream_t st, bool *handled,
-                    int phases)
+                    const double *p, double *stats, double *ws, bool with_ll, bool f32, bool seg, cudaStream_t st,
+                    bool *handled, int phases)
 {
     *handled = true;
     switch (K) {
-        case 1: return launch_em_fused<1>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 2: return launch_em_fused<2>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 3: return launch_em_fused<3>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 4: return launch_em_fused<4>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 5: return launch_em_fused<5>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 6: return launch_em_fused<6>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 7: return launch_em_fused<7>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 8: return launch_em_fused<8>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 9: return launch_em_fused<9>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 10: return launch_em_fused<10>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 11: return launch_em_fused<11>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 12: return launch_em_fused<12>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 13: return launch_em_fused<13>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 14: return launch_em_fused<14>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 15: return launch_em_fused<15>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
-        case 16: return launch_em_fused<16>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, phases, st);
+        case 1: return launch_em_fused<1>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 2: return launch_em_fused<2>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 3: return launch_em_fused<3>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 4: return launch_em_fused<4>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 5: return launch_em_fused<5>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 6: return launch_em_fused<6>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 7: return launch_em_fused<7>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 8: return launch_em_fused<8>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 9: return launch_em_fused<9>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 10: return launch_em_fused<10>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 11: return launch_em_fused<11>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 12: return launch_em_fused<12>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 13: return launch_em_fused<13>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 14: return launch_em_fused<14>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 15: return launch_em_fused<15>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 16: return launch_em_fused<16>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
         default: *handled = false; return 0;
     }
 }
