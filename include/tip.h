@@ -49,9 +49,10 @@ extern "C" {
 #define TIP_EM_FORCE_GENERIC 1u /* use the any-K kernels even where a K-specialised kernel exists */
 #define TIP_EM_FP32_COMPUTE 2u  /* K <= 10: the two K^3 contractions of the E-step in fp32 (FFMA), everything that
                                    is accumulated across links in fp64; results within 1e-5 of the fp64 mode */
-#define TIP_EM_GENE_SEGMENTED 8u /* K = 5..16, fp64: contract p with theta once per (gene, rating) so that a link costs
+#define TIP_EM_GENE_SEGMENTED 8u /* K >= 5, fp64: contract p with theta once per (gene, rating) so that a link costs
                                    2K^2 instead of 2K^3 FMA (same results to rounding); the kernel is then bound by
-                                   the theta gather and the reductions, not by the FMA pipe */
+                                   the theta gather and the reductions, not by the FMA pipe.  K = 17..32 always
+                                   runs this formulation (its only specialised kernel) */
 #define TIP_EM_WITH_LOGLIK 4u   /* also accumulate the log-likelihood by-product (last stats slot); off by
                                    default because the log costs ~2 % of a K=10 step and the training loop only
                                    needs the likelihood every `fcheck` iterations (tip_loglik) */

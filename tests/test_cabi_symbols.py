@@ -30,7 +30,8 @@ def test_trivial_host_only_calls(lib):
     assert lib.tip_em_workspace_bytes(100, 10, 3200, 0, ctypes.byref(nb)) == 0 and nb.value == 2 * 100 * 100 * 8
     assert lib.tip_em_workspace_bytes(100, 4, 3200, 0, ctypes.byref(nb)) == 0 and nb.value == 0
     assert lib.tip_em_workspace_bytes(100, 16, 3200, 0, ctypes.byref(nb)) == 0 and nb.value == 2 * 100 * 256 * 8
-    assert lib.tip_em_workspace_bytes(100, 20, 3200, 0, ctypes.byref(nb)) == 0 and nb.value == 3200 * 8
+    assert lib.tip_em_workspace_bytes(100, 20, 3200, 0, ctypes.byref(nb)) == 0 and nb.value == 4 * 100 * 400 * 8
+    assert lib.tip_em_workspace_bytes(100, 20, 3200, 1, ctypes.byref(nb)) == 0 and nb.value == 3200 * 8
     assert lib.tip_em_workspace_bytes(100, 33, 3200, 0, ctypes.byref(nb)) != 0
     assert b"bad arguments" in lib.tip_last_error()
 

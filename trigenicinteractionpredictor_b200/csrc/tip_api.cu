@@ -19,12 +19,13 @@ void set_error(const char *fmt, ...)
 }
 
 static bool valid_K(int K) { return K >= 1 && K <= TIP_MAX_K; }
-// K-specialised kernels: K <= 10 always; K = 11..16 in plain fp64 mode (no by-product, no fp32 mode)
+// K-specialised kernels: K <= 10 always; K = 11..16 in plain fp64 mode (no by-product, no fp32 mode);
+// K = 17..32 in the gene-segmented formulation (the only specialised one there)
 static bool uses_tuned(int K, unsigned flags)
 {
     if (flags & TIP_EM_FORCE_GENERIC) return false;
     if (K <= 10) return true;
-    return K <= 16 && !(flags & (TIP_EM_WITH_LOGLIK | TIP_EM_FP32_COMPUTE));
+    return !(flags & (TIP_EM_WITH_LOGLIK | TIP_EM_FP32_COMPUTE));
 }
 static bool seg_flag(unsigned flags) { return (flags & TIP_EM_GENE_SEGMENTED) != 0; }
 
@@ -56,8 +57,8 @@ extern "C" int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int
     TIP_REQUIRE(d_theta && d_p && d_stats && (d_rows || n_rows == 0), "tip_em_step: null pointer");
     TIP_REQUIRE(!(flags & TIP_EM_FP32_COMPUTE) || (K <= 10 && !(flags & (TIP_EM_FORCE_GENERIC | TIP_EM_WITH_LOGLIK))),
                 "tip_em_step: TIP_EM_FP32_COMPUTE exists for the K <= 10 kernels only, without FORCE_GENERIC / WITH_LOGLIK");
-    TIP_REQUIRE(!seg_flag(flags) || (K <= 16 && !(flags & (TIP_EM_FORCE_GENERIC | TIP_EM_WITH_LOGLIK | TIP_EM_FP32_COMPUTE))),
-                "tip_em_step: TIP_EM_GENE_SEGMENTED exists for the K <= 16 fp64 kernels only, without other mode flags");
+    TIP_REQUIRE(!seg_flag(flags) || !(flags & (TIP_EM_FORCE_GENERIC | TIP_EM_WITH_LOGLIK | TIP_EM_FP32_COMPUTE)),
+                "tip_em_step: TIP_EM_GENE_SEGMENTED cannot be combined with other mode flags");
     TIP_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * (size_t)tip_stats_len(P, K), st));
     if (n_rows == 0) return 0;
     const int4 *rows = reinterpret_cast<const int4 *>(d_rows);

@@ -43,7 +43,7 @@ namespace tip {
 constexpr int kPSlots = 3;
 constexpr int kPSlotDoubles = 2000;
 constexpr int kPBankDoubles = 8064;
-constexpr int kMaxTunedK = 16;
+constexpr int kMaxTunedK = 32;      // K = 17..32: gene-segmented formulation only
 __constant__ double c_pem[kPBankDoubles];
 __device__ double g_pstage[kPBankDoubles];
 
@@ -320,53 +320,62 @@ __global__ void __launch_bounds__(32, MINB)
             // p index (units of T) of this tile's rating inside the constant bank
             const int pbase = r ? p_off1 : p_off0;
             const T *cp = reinterpret_cast<const T *>(c_pem);
-            T tb[KP], tc[KP], v[K], w[KP];
+            // registers: th_b / v only on the K^3 path; the gene-segmented path reads th_b[b] from the stage as
+            // it goes and parks the unscaled slot-b contribution in cbuf, so it needs 2K doubles of state (K <= 32)
+            T tb[SEG ? 2 : KP], tc[KP], v[SEG ? 1 : K], w[KP];
 #pragma unroll
             for (int k = 0; k < KP; k += 2) {
-                const double2 b2 = *reinterpret_cast<const double2 *>(row + KP + k);
                 const double2 c2 = *reinterpret_cast<const double2 *>(row + 2 * KP + k);
-                tb[k] = (T)b2.x; tb[k + 1] = (T)b2.y;
                 tc[k] = (T)c2.x; tc[k + 1] = (T)c2.y;
                 w[k] = (T)0; w[k + 1] = (T)0;
+                if constexpr (!SEG) {
+                    const double2 b2 = *reinterpret_cast<const double2 *>(row + KP + k);
+                    tb[k] = (T)b2.x; tb[k + 1] = (T)b2.y;
+                }
             }
+            if constexpr (!SEG) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) v[k] = (T)0;
+                for (int k = 0; k < K; ++k) v[k] = (T)0;
+            }
             T dsum = (T)0;
             if constexpr (SEG) {
                 // per-lane pointer to Z of this link's slot-a gene and rating
                 const double *Zrow = Zg + ((int64_t)r_v * P + me.x) * (K * K);
-#pragma unroll
+#pragma unroll 2
                 for (int b = 0; b < K; ++b) {
+                    const T tbb = (T)row[KP + b];
                     T y0 = (T)0, y1 = (T)0;
 #pragma unroll
                     for (int c = 0; c < K; c += 2) {
                         if constexpr (K % 2 == 0) {
                             const double2 z = __ldg(reinterpret_cast<const double2 *>(Zrow + b * K + c));
                             y0 = fma((T)z.x, tc[c], y0);
-                            w[c] = fma(tb[b], (T)z.x, w[c]);
+                            w[c] = fma(tbb, (T)z.x, w[c]);
                             y1 = fma((T)z.y, tc[c + 1], y1);
-                            w[c + 1] = fma(tb[b], (T)z.y, w[c + 1]);
+                            w[c + 1] = fma(tbb, (T)z.y, w[c + 1]);
                         } else {
                             const T z0 = (T)__ldg(Zrow + b * K + c);
                             y0 = fma(z0, tc[c], y0);
-                            w[c] = fma(tb[b], z0, w[c]);
+                            w[c] = fma(tbb, z0, w[c]);
                             if (c + 1 < K) {
                                 const T z1 = (T)__ldg(Zrow + b * K + c + 1);
                                 y1 = fma(z1, tc[c + 1], y1);
-                                w[c + 1] = fma(tb[b], z1, w[c + 1]);
+                                w[c + 1] = fma(tbb, z1, w[c + 1]);
                             }
                         }
                     }
-                    v[b] = y0 + y1;
-                    dsum = fma(tb[b], v[b], dsum);
+                    const T tby = tbb * (y0 + y1);
+                    dsum += tby;
+                    crow[CA + b] = (double)tby;  // unscaled slot-b contribution, multiplied by s below
                 }
             }
             const double *ta_p = row;  // walked separately so that `a` only ever indexes the constant bank
             double *tt_p = crow;
             // (A per-lane ld.const prefetch of the next a-slice was tried against the 88 % constant-cache hit rate
             // ncu reports: the divergent constant access serialises and costs 35 % - not kept.)
+            if constexpr (!SEG)
 #pragma unroll 1
-            for (int a = 0; a < (SEG ? 0 : K); ++a) {
+            for (int a = 0; a < K; ++a) {
                 const T ta = (T)(*ta_p++);
                 const int pa = pbase + a * (K * KP);
                 T u = (T)0;
@@ -394,6 +403,7 @@ __global__ void __launch_bounds__(32, MINB)
                 dsum += tt;
                 if constexpr (C::kPrivateS) *tt_p++ = (double)tt;  // slot-a contribution (K >= 5: from M_g in em_finalize_kernel)
             }
+            (void)ta_p; (void)tt_p; (void)cp; (void)pbase;
             const double d = TIP_EPS + (double)dsum;
             // s = cnt / d.  d lies in [1e-10, ~1]: an fp32 reciprocal seed and two Newton steps give 1/d to the
             // last ulp or two (far inside the 1e-9 budget) in ~8 instructions instead of the ~30 of an IEEE divide
@@ -411,10 +421,17 @@ __global__ void __launch_bounds__(32, MINB)
                     *reinterpret_cast<double2 *>(crow + k) = ca;
                 }
                 // theta values re-read in fp64 from the stage (T = float only rounded them for the contractions)
-                const double2 b2 = *reinterpret_cast<const double2 *>(row + KP + k);
                 const double2 c2 = *reinterpret_cast<const double2 *>(row + 2 * KP + k);
-                const double vb1 = (k + 1 < K) ? (double)v[k + 1] : 0.0;
-                *reinterpret_cast<double2 *>(crow + CA + k) = make_double2(s * b2.x * (double)v[k], s * b2.y * vb1);
+                if constexpr (SEG) {
+                    double2 cb2 = *reinterpret_cast<double2 *>(crow + CA + k);
+                    cb2.x *= s;
+                    cb2.y = (k + 1 < K) ? cb2.y * s : 0.0;
+                    *reinterpret_cast<double2 *>(crow + CA + k) = cb2;
+                } else {
+                    const double2 b2 = *reinterpret_cast<const double2 *>(row + KP + k);
+                    const double vb1 = (k + 1 < K) ? (double)v[k + 1] : 0.0;
+                    *reinterpret_cast<double2 *>(crow + CA + k) = make_double2(s * b2.x * (double)v[k], s * b2.y * vb1);
+                }
                 const double sc0 = s * c2.x, sc1 = s * c2.y;
                 *reinterpret_cast<double2 *>(crow + CA + KP + k) = make_double2(sc0 * (double)w[k], sc1 * (double)w[k + 1]);
                 *reinterpret_cast<double2 *>(row + 2 * KP + k) = make_double2(sc0, sc1);
@@ -664,6 +681,98 @@ constexpr size_t fin_smem_bytes()
     return sizeof(double) * (2 * K * K * K + fin_chunk<K>() * K + 2 * fin_chunk<K>() * K * K);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-gene finish for K > 16 (run-time K, gene-segmented mode only): the same two contractions as
+// em_finalize_kernel, shaped as small tiled GEMMs because p (2*K^3 doubles) no longer fits shared memory.
+//   fin_S_generic_kernel   S[r][a][bc]  += sum_g theta[g][a] * M_r[g][bc]          thread = bc, K accumulators
+//   fin_A_generic_kernel   Ntheta[g][a] += theta[g][a] * sum_r sum_bc p[a][bc][r] * M_r[g][bc]   thread = (gene, a)
+// ---------------------------------------------------------------------------------------------
+constexpr int kFinGChunkGenes = 32;
+
+__global__ void __launch_bounds__(128)
+    fin_S_generic_kernel(int P, int K, int genes_per_cta, const double *__restrict__ theta, const double *__restrict__ Mg,
+                         double *__restrict__ stats)
+{
+    __shared__ double sT[kFinGChunkGenes][TIP_MAX_K];
+    const int KK = K * K, K3 = KK * K;
+    const int r = blockIdx.z;
+    const int bc = blockIdx.x * 128 + threadIdx.x;
+    const int g_lo = blockIdx.y * genes_per_cta, g_hi = (g_lo + genes_per_cta < P) ? g_lo + genes_per_cta : P;
+    double acc[TIP_MAX_K];
+#pragma unroll
+    for (int a = 0; a < TIP_MAX_K; ++a) acc[a] = 0.0;
+    const double *Mr = Mg + (int64_t)r * P * KK;
+    for (int g0 = g_lo; g0 < g_hi; g0 += kFinGChunkGenes) {
+        const int ng = (g_hi - g0 < kFinGChunkGenes) ? g_hi - g0 : kFinGChunkGenes;
+        __syncthreads();
+        for (int e = threadIdx.x; e < ng * K; e += 128) sT[e / K][e % K] = __ldg(theta + (int64_t)g0 * K + e);
+        __syncthreads();
+        if (bc < KK) {
+#pragma unroll 4
+            for (int gi = 0; gi < ng; ++gi) {
+                const double m = __ldg(Mr + (int64_t)(g0 + gi) * KK + bc);
+#pragma unroll
+                for (int a = 0; a < TIP_MAX_K; ++a)
+                    if (a < K) acc[a] = fma(sT[gi][a], m, acc[a]);
+            }
+        }
+    }
+    if (bc < KK) {
+        double *S = stats + stats_off_S(P, K) + (int64_t)r * K3;
+#pragma unroll
+        for (int a = 0; a < TIP_MAX_K; ++a)
+            if (a < K) red_add_f64_nz(S + (int64_t)a * KK + bc, acc[a]);
+    }
+}
+
+constexpr int kFinAGenes = 8, kFinATile = 64;
+
+__global__ void __launch_bounds__(kFinAGenes *TIP_MAX_K)
+    fin_A_generic_kernel(int P, int K, const double *__restrict__ theta, const double *__restrict__ p,
+                         const double *__restrict__ Mg, double *__restrict__ stats)
+{
+    __shared__ double sP[kFinATile][2][TIP_MAX_K];      // p[a][bc][r] tile, a contiguous
+    __shared__ double sM[kFinAGenes][kFinATile][2];     // M_r[g][bc] tile
+    const int KK = K * K;
+    const int a = threadIdx.x % TIP_MAX_K, gi = threadIdx.x / TIP_MAX_K;
+    const int g = blockIdx.x * kFinAGenes + gi;
+    const int nthreads = kFinAGenes * TIP_MAX_K;
+    double t = 0.0;
+    for (int bc0 = 0; bc0 < KK; bc0 += kFinATile) {
+        const int nb = (KK - bc0 < kFinATile) ? KK - bc0 : kFinATile;
+        __syncthreads();
+        for (int e = threadIdx.x; e < nb * 2 * K; e += nthreads) {
+            const int aa = e / (nb * 2), rem = e - aa * (nb * 2), j = rem >> 1, rr = rem & 1;   // p[aa][bc0+j][rr] contiguous in (j, rr)
+            sP[j][rr][aa] = __ldg(p + ((int64_t)aa * KK + bc0 + j) * 2 + rr);
+        }
+        for (int e = threadIdx.x; e < kFinAGenes * nb * 2; e += nthreads) {
+            const int gg = e / (nb * 2), rem = e - gg * (nb * 2), rr = rem / nb, j = rem - rr * nb;
+            const int gene = blockIdx.x * kFinAGenes + gg;
+            sM[gg][j][rr] = gene < P ? __ldg(Mg + ((int64_t)rr * P + gene) * KK + bc0 + j) : 0.0;
+        }
+        __syncthreads();
+        if (a < K) {
+#pragma unroll 8
+            for (int j = 0; j < nb; ++j) t = fma(sP[j][1][a], sM[gi][j][1], fma(sP[j][0][a], sM[gi][j][0], t));
+        }
+    }
+    if (a < K && g < P) red_add_f64_nz(stats + (int64_t)g * K + a, __ldg(theta + (int64_t)g * K + a) * t);
+}
+
+static int launch_finalize_generic(int P, int K, const double *theta, const double *p, const double *Mg, double *stats,
+                                   cudaStream_t st)
+{
+    const int KK = K * K;
+    const int chunks = 24;
+    const int genes_per_cta = (P + chunks - 1) / chunks;
+    fin_S_generic_kernel<<<dim3((KK + 127) / 128, (P + genes_per_cta - 1) / genes_per_cta, 2), 128, 0, st>>>(
+        P, K, genes_per_cta, theta, Mg, stats);
+    TIP_CHECK_CUDA(cudaGetLastError());
+    fin_A_generic_kernel<<<(P + kFinAGenes - 1) / kFinAGenes, kFinAGenes * TIP_MAX_K, 0, st>>>(P, K, theta, p, Mg, stats);
+    TIP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int g_slot_counter = 0;
 
 // TIP_EM_VARIANT (environment, read once) selects resident warps per SM / gather buffering for tuning runs:
@@ -723,8 +832,8 @@ static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_row
 size_t em_tuned_workspace_bytes(int P, int K, bool seg)
 {
     if (K <= 4 || K > kMaxTunedK) return 0;
-    // M_g[r][gene][b][c], followed by Z_g[r][gene][b][c] in the gene-segmented mode
-    return sizeof(double) * 2 * (size_t)P * K * K * (seg ? 2 : 1);
+    // M_g[r][gene][b][c], followed by Z_g[r][gene][b][c] in the gene-segmented mode (always for K > 16)
+    return sizeof(double) * 2 * (size_t)P * K * K * ((seg || K > 16) ? 2 : 1);
 }
 
 // ratings [r_lo, r_lo + n_r) of p -> E-step layout -> constant bank at double-offset base_d (stream-ordered)
@@ -845,6 +954,29 @@ static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_ro
         em_finalize_kernel<K><<<grid, kFinThreads, fin_smem_bytes<K>(), st>>>(P, theta, p, ws, stats);
         TIP_CHECK_CUDA(cudaGetLastError());
     }
+    return 0;
+}
+
+// K = 17..32: only the gene-segmented formulation exists (p does not fit the constant bank, and 4K doubles of
+// per-link state do not fit the register file); same phases as launch_em_fused
+template <int K>
+static int launch_em_seg_large(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
+                               const double *p, double *stats, double *ws, int phases, cudaStream_t st)
+{
+    if (phases & kPhaseBegin) {
+        const int64_t n = 2ll * P * K * K;
+        const int threads = 256;
+        int64_t want = (n + threads - 1) / threads;
+        const int grid = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
+        seg_prep_kernel<<<grid, threads, 0, st>>>(P, K, theta, p, ws + 2 * (size_t)P * K * K);
+        TIP_CHECK_CUDA(cudaGetLastError());
+        TIP_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)P * K * K, st));
+    }
+    if ((phases & kPhaseRun) && n_rows > 0) {
+        const int rc = launch_variant<K, 1, 8, false, double, true>(P, rows, n_rows, n_rows_r0, theta, 0, 0, stats, ws, st);
+        if (rc != 0) return rc;
+    }
+    if (phases & kPhaseEnd) return launch_finalize_generic(P, K, theta, p, ws, stats, st);
     return 0;
 }
 
@@ -1000,6 +1132,22 @@ int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_ro
         case 14: return launch_em_fused<14>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
         case 15: return launch_em_fused<15>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
         case 16: return launch_em_fused<16>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, with_ll, f32, seg, phases, st);
+        case 17: return launch_em_seg_large<17>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 18: return launch_em_seg_large<18>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 19: return launch_em_seg_large<19>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 20: return launch_em_seg_large<20>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 21: return launch_em_seg_large<21>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 22: return launch_em_seg_large<22>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 23: return launch_em_seg_large<23>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 24: return launch_em_seg_large<24>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 25: return launch_em_seg_large<25>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 26: return launch_em_seg_large<26>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 27: return launch_em_seg_large<27>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 28: return launch_em_seg_large<28>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 29: return launch_em_seg_large<29>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 30: return launch_em_seg_large<30>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 31: return launch_em_seg_large<31>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
+        case 32: return launch_em_seg_large<32>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, phases, st);
         default: *handled = false; return 0;
     }
 }

@@ -138,7 +138,7 @@ class EMEngine:
         _cabi.check(self.lib.tip_em_step(self.P, self.K, _ptr(t.rows), t.n_rows, t.n_rows_r0, _ptr(self.theta),
                                          _ptr(self.p), _ptr(stats), _ptr(self.em_ws), self.em_ws_bytes,
                                          self.flags, self._stream()), "tip_em_step")
-        self.launches += 3 if (4 < self.K <= 16 and not (self.flags & _cabi.TIP_EM_FORCE_GENERIC)) else 2
+        self.launches += 3 if (self.K > 4 and not (self.flags & _cabi.TIP_EM_FORCE_GENERIC)) else 2
 
     def normalise(self):
         _cabi.check(self.lib.tip_normalise(self.P, self.K, _ptr(self.stats), _ptr(self.train.deg), _ptr(self.theta),
