@@ -95,8 +95,9 @@ int tip_normalise(int P, int K, const double *d_stats, const int32_t *d_deg, dou
 /* ---- Model.compute_likelihood (TIP.py:952-974) ----
  * *d_out = sum_rows count * log(eps + sum_abc th th th p_r).  Deterministic summation order.
  * Rows as packed by tip_pack_rows (n_rows_r0 = h_part[0]); flags: TIP_EM_FORCE_GENERIC selects the any-K kernel.
- * d_ws: tip_loglik_workspace_bytes() bytes of scratch. */
-size_t tip_loglik_workspace_bytes(void);
+ * d_ws: tip_loglik_workspace_bytes(P, K) bytes of scratch (per-CTA partials; for K > 10 also the per-gene
+ *       contraction Z = theta . p of the gene-segmented formulation). */
+size_t tip_loglik_workspace_bytes(int P, int K);
 int tip_loglik(int P, int K, const void *d_rows, int64_t n_rows, int64_t n_rows_r0, const double *d_theta,
                const double *d_p, double *d_out, void *d_ws, unsigned flags, void *stream);
 

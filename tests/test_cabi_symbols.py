@@ -25,7 +25,8 @@ def test_trivial_host_only_calls(lib):
     assert lib.tip_abi_version() == 1
     assert lib.tip_stats_len(6000, 10) == 6000 * 10 + 2000 + 1
     assert lib.tip_rows_capacity(1000) >= 2 * 1000 + 62
-    assert lib.tip_loglik_workspace_bytes() > 0
+    assert lib.tip_loglik_workspace_bytes(100, 10) > 0
+    assert lib.tip_loglik_workspace_bytes(100, 20) >= lib.tip_loglik_workspace_bytes(100, 10) + 2 * 100 * 400 * 8
     nb = ctypes.c_size_t(0)
     assert lib.tip_em_workspace_bytes(100, 10, 3200, 0, ctypes.byref(nb)) == 0 and nb.value == 2 * 100 * 100 * 8
     assert lib.tip_em_workspace_bytes(100, 4, 3200, 0, ctypes.byref(nb)) == 0 and nb.value == 0

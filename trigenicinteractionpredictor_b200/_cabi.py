@@ -35,7 +35,7 @@ SIGNATURES = {
     "tip_em_step": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                             c_uint, c_void_p]),
     "tip_normalise": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "tip_loglik_workspace_bytes": (c_size_t, []),
+    "tip_loglik_workspace_bytes": (c_size_t, [c_int, c_int]),
     "tip_loglik": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_uint,
                            c_void_p]),
     "tip_score": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

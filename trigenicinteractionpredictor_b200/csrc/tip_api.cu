@@ -84,7 +84,7 @@ extern "C" int tip_normalise(int P, int K, const double *d_stats, const int32_t 
     return launch_normalise(P, K, d_stats, d_deg, d_theta, d_p, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" size_t tip_loglik_workspace_bytes(void) { return loglik_ws_bytes(); }
+extern "C" size_t tip_loglik_workspace_bytes(int P, int K) { return loglik_ws_bytes(P, K); }
 
 extern "C" int tip_loglik(int P, int K, const void *d_rows, int64_t n_rows, int64_t n_rows_r0, const double *d_theta,
                           const double *d_p, double *d_out, void *d_ws, unsigned flags, void *stream)
@@ -97,7 +97,7 @@ extern "C" int tip_loglik(int P, int K, const void *d_rows, int64_t n_rows, int6
         TIP_CHECK_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), st));
         return 0;
     }
-    return launch_loglik(K, reinterpret_cast<const int4 *>(d_rows), n_rows, n_rows_r0, d_theta, d_p, d_out, d_ws,
+    return launch_loglik(P, K, reinterpret_cast<const int4 *>(d_rows), n_rows, n_rows_r0, d_theta, d_p, d_out, d_ws,
                          (flags & TIP_EM_FORCE_GENERIC) != 0, st);
 }
 

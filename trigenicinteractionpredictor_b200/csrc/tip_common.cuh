@@ -87,13 +87,16 @@ int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_ro
                     const double *p, double *stats, double *ws, bool with_ll, bool f32, bool seg, cudaStream_t st,
                     bool *handled, int phases = 7);
 size_t em_tuned_workspace_bytes(int P, int K, bool seg);
-int launch_loglik(int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
+int launch_loglik(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
                   double *out, void *ws, bool force_generic, cudaStream_t st);
+int launch_loglik_seg(int P, int K, const int4 *rows, int64_t n_rows, const double *theta, const double *p, double *out,
+                      double *partials, unsigned *counter, int max_blocks, double *Zws, cudaStream_t st);
+size_t loglik_seg_workspace_bytes(int P, int K);
 int launch_loglik_tuned(int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
                         double *out, double *partials, unsigned *counter, int max_blocks, cudaStream_t st, bool *handled);
 int launch_score(int K, const int32_t *g1, const int32_t *g2, const int32_t *g3, int64_t T, const double *theta,
                  const double *p, double *scores, cudaStream_t st);
-size_t loglik_ws_bytes();
+size_t loglik_ws_bytes(int P, int K);
 int launch_normalise(int P, int K, const double *stats, const int32_t *deg, double *theta, double *p,
                      cudaStream_t st);
 

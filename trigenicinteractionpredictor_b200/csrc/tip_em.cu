@@ -185,7 +185,7 @@ template <int K, int NBUF, int MINB, bool LL, typename T, bool SEG>
 __global__ void __launch_bounds__(32, MINB)
     em_fused_kernel(int P, const int4 *__restrict__ rows, int n_tiles, int n_tiles_r0, const double *__restrict__ theta,
                     int p_off0, int p_off1, double *__restrict__ stats, double *__restrict__ Mg,
-                    const double *__restrict__ Zg, int dbg)
+                    const double *__restrict__ Zg, int red_scatter)
 {
     using C = EmCfg<K, NBUF>;
     constexpr int KP = C::KP, RS = C::RS, K3 = C::K3, CB = C::CB, RC = C::RC, CA = C::CA;
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(32, MINB)
         __syncwarp();
 
         // ================= scatter theta statistics =================
-        if (!(dbg & 1)) {
+        {
             const int *idw = reinterpret_cast<const int *>(ids);
             if constexpr (C::kPrivateS) {
                 // slot a: run-length pre-reduction.  lane -> (k = lane % K, part = lane / K); each part
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(32, MINB)
                 }
             }
             // slots b, c
-            if (K % 2 == 0 && !(dbg & 4)) {
+            if (K % 2 == 0 && !red_scatter) {
                 // one bulk add-reduction per (link, slot): the 8K-byte row goes to the TMA unit
                 fence_async_smem();
                 if (cnt != 0.0) {
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(32, MINB)
         }
 
         // ====== phase B: M_g[b][c] += th_b[b] * (s th_c[c]), flushed per run of equal slot-a gene ======
-        if constexpr (!C::kPrivateS) if (!(dbg & 2)) {
+        if constexpr (!C::kPrivateS) {
             const int *idw = reinterpret_cast<const int *>(ids);
             double M[CB];
 #pragma unroll
@@ -775,28 +775,28 @@ static int launch_finalize_generic(int P, int K, const double *theta, const doub
 
 static int g_slot_counter = 0;
 
-// TIP_EM_VARIANT (environment, read once) selects resident warps per SM / gather buffering for tuning runs:
-//   0 (default) = 12 warp-CTAs per SM (<=168 regs), single-buffered gather
-//   1 = 8 per SM (<=255 regs), double-buffered      2 = 12 per SM, double-buffered      3 = 16 per SM (<=128 regs)
-// All variants produce the same statistics.
+// TIP_EM_VARIANT=1 (environment, read once): 16 instead of 12 resident warp-CTAs per SM (<=128 registers) for tuning
+// runs; measured equal within noise at K=10.  (A double-buffered gather was measured slower: its shared memory
+// halves the resident warps; the NBUF template parameter keeps that variant buildable.)
 static int em_variant()
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("TIP_EM_VARIANT");
         v = e ? atoi(e) : 0;
-        if (v < 0 || v > 4) v = 0;
+        if (v < 0 || v > 1) v = 0;
     }
     return v;
 }
 
-// TIP_EM_DEBUG (environment): bit 0 skips the theta scatter, bit 1 skips phase B - timing experiments only
-static int em_debug()
+// TIP_EM_SCATTER=red (environment, read once): slot-b/c contributions with per-lane red.global.add.f64 instead of
+// the bulk add-reductions, for A/B timing (measured equal within noise at K=10; both give the same statistics)
+static int em_red_scatter()
 {
     static int v = -1;
     if (v < 0) {
-        const char *e = getenv("TIP_EM_DEBUG");
-        v = e ? atoi(e) : 0;
+        const char *e = getenv("TIP_EM_SCATTER");
+        v = (e && e[0] == 'r') ? 1 : 0;
     }
     return v;
 }
@@ -824,7 +824,7 @@ static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_row
     if (grid < 1) grid = 1;
     em_fused_kernel<K, NBUF, MINB, LL, T, SEG><<<grid, 32, C::SMEM, st>>>(
         P, rows, (int)n_tiles, (int)(n_rows_r0 / 32), theta, p_off0, p_off1, stats, Mg,
-        SEG ? Mg + 2 * (size_t)P * K * K : nullptr, em_debug());
+        SEG ? Mg + 2 * (size_t)P * K * K : nullptr, em_red_scatter());
     TIP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -933,10 +933,7 @@ static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_ro
         rc = run_rows<K, 1, 12, true, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st);
     } else {
         switch (em_variant()) {
-            case 1: rc = run_rows<K, 2, 8, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
-            case 2: rc = run_rows<K, 2, 12, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
-            case 3: rc = run_rows<K, 1, 16, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
-            case 4: rc = run_rows<K, 1, 14, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
+            case 1: rc = run_rows<K, 1, 16, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
             default: rc = run_rows<K, 1, 12, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
         }
     }
@@ -1108,6 +1105,89 @@ int launch_loglik_tuned(int K, const int4 *rows, int64_t n_rows, int64_t n_rows_
         case 10: return launch_loglik_fused<10>(rows, n_rows, n_rows_r0, theta, p, out, partials, counter, max_blocks, st);
         default: *handled = false; return 0;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Model.compute_likelihood for K = 11..32 in the gene-segmented formulation (run-time K):
+//   Z_g = theta_g . p  (seg_prep_kernel),   d = eps + sum_b th_b[b] sum_c Z_a[b][c] th_c[c]     (K^2 FMA per link)
+// Same deterministic reduction of per-CTA partials as loglik_fused_kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32, 16)
+    loglik_seg_kernel(int P, int K, const int4 *__restrict__ rows, int n_tiles, const double *__restrict__ theta,
+                      const double *__restrict__ Zg, double *__restrict__ partials, unsigned *__restrict__ counter,
+                      double *__restrict__ out)
+{
+    extern __shared__ __align__(16) double lsm[];   // [32][2K+1]: th_b | th_c per link (odd stride: conflict-free)
+    const int lane = threadIdx.x, RSL = 2 * K + 1, KK = K * K;
+    unsigned bx_v, gx_v;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(bx_v));
+    asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(gx_v));
+    double ll = 0.0;
+    for (unsigned t = bx_v; t < (unsigned)n_tiles; t += gx_v) {
+        const int4 me = rows[(int64_t)t * 32 + lane];
+        __syncwarp();
+        // gather th_b and th_c of the 32 links (row-contiguous: consecutive lanes read consecutive doubles)
+        for (int e = lane; e < 32 * 2 * K; e += 32) {
+            const int l = e / (2 * K), rem = e - l * 2 * K, slot = rem / K, k = rem - slot * K;
+            // (the shuffled value is evaluated in the SOURCE lane: fetch both slots, select by this lane's slot)
+            const int gb = __shfl_sync(0xffffffffu, me.y, l), gc = __shfl_sync(0xffffffffu, me.z, l);
+            const int gsrc = slot == 0 ? gb : gc;
+            lsm[l * RSL + rem] = __ldg(theta + (int64_t)gsrc * K + k);
+        }
+        __syncwarp();
+        const int cnt = row_count(me.w);
+        const double *Zrow = Zg + ((int64_t)row_rating(me.w) * P + me.x) * KK;
+        const double *tb = lsm + lane * RSL, *tc = tb + K;
+        double dsum = 0.0;
+        for (int b = 0; b < K; ++b) {
+            double y0 = 0.0, y1 = 0.0;
+            int c = 0;
+            for (; c + 1 < K; c += 2) {
+                y0 = fma(__ldg(Zrow + b * K + c), tc[c], y0);
+                y1 = fma(__ldg(Zrow + b * K + c + 1), tc[c + 1], y1);
+            }
+            if (c < K) y0 = fma(__ldg(Zrow + b * K + c), tc[c], y0);
+            dsum = fma(tb[b], y0 + y1, dsum);
+        }
+        if (cnt != 0) ll += (double)cnt * log(TIP_EPS + dsum);
+    }
+    ll = warp_sum(ll);
+    __shared__ bool last;
+    if (lane == 0) {
+        partials[bx_v] = ll;
+        __threadfence();
+        last = (atomicAdd(counter, 1u) == gx_v - 1);
+    }
+    __syncwarp();
+    if (last) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned i = lane; i < gx_v; i += 32) t += reinterpret_cast<volatile double *>(partials)[i];
+        t = warp_sum(t);
+        if (lane == 0) {
+            *out = t;
+            *counter = 0;
+        }
+    }
+}
+
+size_t loglik_seg_workspace_bytes(int P, int K) { return K > 10 ? sizeof(double) * 2 * (size_t)P * K * K : 0; }
+
+int launch_loglik_seg(int P, int K, const int4 *rows, int64_t n_rows, const double *theta, const double *p, double *out,
+                      double *partials, unsigned *counter, int max_blocks, double *Zws, cudaStream_t st)
+{
+    const int64_t n = 2ll * P * K * K;
+    int64_t want = (n + 255) / 256;
+    seg_prep_kernel<<<(int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16), 256, 0, st>>>(P, K, theta, p, Zws);
+    TIP_CHECK_CUDA(cudaGetLastError());
+    const int64_t n_tiles = n_rows / 32;
+    int64_t cap = (int64_t)sm_count() * 16;
+    if (cap > max_blocks) cap = max_blocks;
+    const int grid = (int)(n_tiles < cap ? (n_tiles < 1 ? 1 : n_tiles) : cap);
+    const size_t smem = sizeof(double) * 32 * (2 * K + 1);
+    loglik_seg_kernel<<<grid, 32, smem, st>>>(P, K, rows, (int)n_tiles, theta, Zws, partials, counter, out);
+    TIP_CHECK_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kGenWarps *kWarp)
     }
 }
 
-int launch_loglik(int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
+int launch_loglik(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
                   double *out, void *ws, bool force_generic, cudaStream_t st)
 {
     double *partials = reinterpret_cast<double *>(ws);
@@ -257,6 +257,11 @@ int launch_loglik(int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, co
         const int rc = launch_loglik_tuned(K, rows, n_rows, n_rows_r0, theta, p, out, partials, counter, kLlMaxBlocks, st,
                                            &handled);
         if (rc != 0 || handled) return rc;
+        if (K > 10 && P > 0) {
+            // Z workspace follows the partials/counter header (see loglik_ws_bytes)
+            double *Zws = reinterpret_cast<double *>(reinterpret_cast<char *>(ws) + loglik_ws_bytes(0, 0));
+            return launch_loglik_seg(P, K, rows, n_rows, theta, p, out, partials, counter, kLlMaxBlocks, Zws, st);
+        }
     }
     int64_t want = (n_rows + kGenWarps - 1) / kGenWarps;
     int grid = (int)((want < (int64_t)sm_count() * 4) ? want : (int64_t)sm_count() * 4);
@@ -279,6 +284,10 @@ int launch_score(int K, const int32_t *g1, const int32_t *g2, const int32_t *g3,
     return 0;
 }
 
-size_t loglik_ws_bytes() { return kLlMaxBlocks * sizeof(double) + 64; }
+size_t loglik_ws_bytes(int P, int K)
+{
+    const size_t header = (kLlMaxBlocks * sizeof(double) + 64 + 255) / 256 * 256;
+    return header + loglik_seg_workspace_bytes(P, K);
+}
 
 }  // namespace tip

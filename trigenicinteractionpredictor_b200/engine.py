@@ -48,7 +48,8 @@ class EMEngine:
             self.p = torch.empty(2 * self.K ** 3, dtype=torch.float64, device=self.device)
             self.stats = torch.zeros(self.n_stats, dtype=torch.float64, device=self.device)
             self.ll_out = torch.zeros(1, dtype=torch.float64, device=self.device)
-            self.ll_ws = torch.empty(int(self.lib.tip_loglik_workspace_bytes()), dtype=torch.uint8, device=self.device)
+            self.ll_ws = torch.empty(int(self.lib.tip_loglik_workspace_bytes(self.P, self.K)), dtype=torch.uint8,
+                                     device=self.device)
         # link shards: how the statistics are summed across ranks - "peer" (NVLink peer memory, fused into the
         # M-step kernel) or "nccl" (torch.distributed allreduce)
         self.peer = None
