@@ -418,46 +418,79 @@ def _read_peaks():
 
 
 def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
-    """Same metric with HOST buffers: per step copy rows + theta + p in, run one iteration, copy theta + p out."""
+    """Same metric with HOST buffers: per step copy rows + deg + theta + p in, run one iteration, copy theta + p out.
+    The rows travel in the 8-byte host format (tip_rows_compact_host) and are expanded on the device as they land;
+    the 16-byte format is timed beside it (`rows16`)."""
     import numpy as np
     import torch
+    from trigenicinteractionpredictor_b200 import _cabi
     P, K = eng.P, eng.K
     rows_h = eng.train.rows.cpu().pin_memory()
+    n_rows = eng.train.n_rows
+    rows8_h = torch.empty(max(n_rows, 1), dtype=torch.int64).pin_memory()
+    rc = lib.tip_rows_compact_host(rows_h.data_ptr(), n_rows, rows8_h.data_ptr())
+    if rc != 0:
+        raise RuntimeError(lib.tip_last_error())
     deg_h = eng.train.deg.cpu().pin_memory()
     th_h = torch.from_numpy(np.ascontiguousarray(theta0)).pin_memory()
     p_h = torch.from_numpy(np.ascontiguousarray(pr0)).pin_memory()
-    h2d = rows_h.numel() * 4 + deg_h.numel() * 4 + th_h.numel() * 8 + p_h.numel() * 8
+    fixed = deg_h.numel() * 4 + th_h.numel() * 8 + p_h.numel() * 8
     d2h = th_h.numel() * 8 + p_h.numel() * 8
     steps = args.steps
-    if world == 1:
+
+    def make_step(compact):
+        if world == 1:
+            src = rows8_h if compact else rows_h
+            fl = _cabi.TIP_ROWS_COMPACT8 if compact else 0
+
+            def step():
+                rc = lib.tip_em_iterations_host(P, K, src.data_ptr(), n_rows, eng.train.n_rows_r0,
+                                                deg_h.data_ptr(), th_h.data_ptr(), p_h.data_ptr(), 1, fl)
+                if rc != 0:
+                    raise RuntimeError(lib.tip_last_error())
+            return step
+        rows8_d = torch.empty(max(n_rows, 1), dtype=torch.int64, device=dev) if compact else None
+
         def step():
-            rc = lib.tip_em_iterations_host(P, K, rows_h.data_ptr(), eng.train.n_rows, eng.train.n_rows_r0,
-                                            deg_h.data_ptr(), th_h.data_ptr(), p_h.data_ptr(), 1, 0)
-            if rc != 0:
-                raise RuntimeError(lib.tip_last_error())
-        api = "tip_em_iterations_host (C ABI, pinned host buffers)"
-    else:
-        def step():
-            eng.train.rows.copy_(rows_h, non_blocking=True)
+            if compact:
+                rows8_d.copy_(rows8_h, non_blocking=True)
+                rc = lib.tip_rows_expand(rows8_d.data_ptr(), eng.train.rows.data_ptr(), n_rows,
+                                         torch.cuda.current_stream(dev).cuda_stream)
+                if rc != 0:
+                    raise RuntimeError(lib.tip_last_error())
+            else:
+                eng.train.rows.copy_(rows_h, non_blocking=True)
+            eng.train.deg.copy_(deg_h, non_blocking=True)
             eng.theta.copy_(th_h.view(-1), non_blocking=True)
             eng.p.copy_(p_h.view(-1), non_blocking=True)
             eng.em_iteration()
             th_h.view(-1).copy_(eng.theta, non_blocking=True)
             p_h.view(-1).copy_(eng.p, non_blocking=True)
             torch.cuda.synchronize(dev)
-        api = "EMEngine.em_iteration with pinned host copies (link-sharded, %s exchange)" % args.exchange
-    for _ in range(3):
-        step()
-    tdist.barrier(group)
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    dt = tdist.max_over_ranks(dt, device=dev, group=group)
-    return {"value": L_total * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": 1e3 * dt / steps, "api": api}
+        return step
+
+    def timed(step):
+        for _ in range(3):
+            step()
+        tdist.barrier(group)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize(dev)
+        return tdist.max_over_ranks(time.perf_counter() - t0, device=dev, group=group)
+
+    dt16 = timed(make_step(False))
+    dt = timed(make_step(True))
+    if world == 1:
+        api = "tip_em_iterations_host (C ABI, pinned host buffers, 8-byte rows: TIP_ROWS_COMPACT8)"
+    else:
+        api = ("EMEngine.em_iteration with pinned host copies, 8-byte rows + tip_rows_expand (link-sharded, %s exchange)"
+               % args.exchange)
+    return {"value": L_total * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(n_rows * 8 + fixed),
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / steps, "api": api,
+            "rows16": {"value": L_total * steps / dt16, "ms_per_step": 1e3 * dt16 / steps,
+                       "h2d_bytes_per_step": int(n_rows * 16 + fixed)}}
 
 
 def main():

@@ -57,6 +57,9 @@ extern "C" {
                                    default because the log costs ~2 % of a K=10 step and the training loop only
                                    needs the likelihood every `fcheck` iterations (tip_loglik) */
 
+/* flag for tip_em_iterations_host only: h_rows holds the 8-byte rows of tip_rows_compact_host */
+#define TIP_ROWS_COMPACT8 16u
+
 int tip_abi_version(void);
 const char *tip_last_error(void);
 
@@ -122,6 +125,15 @@ int tip_metrics(const double *d_scores, const int32_t *d_labels, int64_t T, int6
  * This is the call bench.py times for the end-to-end number. */
 int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t n_rows, int64_t n_rows_r0,
                            const int32_t *h_deg, double *h_theta, double *h_p, int n_iter, unsigned flags);
+
+/* 8-byte host rows for the entry above (flags | TIP_ROWS_COMPACT8): halves the host->device traffic, which is what
+ * bounds a single host-buffer iteration.  row = c | b << 20 | a << 40 | rating << 60 | count << 61; the device
+ * expands them to the 16-byte rows as each chunk lands.  Pure host code (no CUDA call).  Fails (-1) when a gene id
+ * needs more than 20 bits or a count exceeds 7 (duplicated input lines, TIP.py:361-368): use the 16-byte rows then. */
+int tip_rows_compact_host(const void *h_rows, int64_t n_rows, uint64_t *h_rows8);
+/* device side of the same format: d_rows8[n_rows] (8 B each) -> d_rows[n_rows] (16 B each), for callers that do
+ * their own host->device copies (bench.py's link-sharded end-to-end leg) */
+int tip_rows_expand(const void *d_rows8, void *d_rows, int64_t n_rows, void *stream);
 
 /* ---- link shards over NVLink peer memory (replaces the NCCL allreduce between E-step and M-step) ----
  * One process per GPU.  Each rank shares its statistics buffers and a flag array with its peers:

@@ -37,6 +37,32 @@ def test_trivial_host_only_calls(lib):
     assert b"bad arguments" in lib.tip_last_error()
 
 
+def test_rows_compact_host_format(lib):
+    """8-byte host rows: pure host packing (no CUDA call); c | b<<20 | a<<40 | rating<<60 | count<<61."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    n = 257
+    rows = np.empty((n, 4), dtype=np.int32)
+    rows[:, :3] = rng.integers(0, 1 << 20, size=(n, 3))
+    cnt, rat = rng.integers(0, 8, size=n), rng.integers(0, 2, size=n)
+    rows[:, 3] = (cnt << 1) | rat
+    out = np.zeros(n, dtype=np.uint64)
+    assert lib.tip_rows_compact_host(rows.ctypes.data, n, out.ctypes.data) == 0
+    m = np.uint64((1 << 20) - 1)
+    assert np.array_equal(out & m, rows[:, 2].astype(np.uint64))
+    assert np.array_equal((out >> np.uint64(20)) & m, rows[:, 1].astype(np.uint64))
+    assert np.array_equal((out >> np.uint64(40)) & m, rows[:, 0].astype(np.uint64))
+    assert np.array_equal((out >> np.uint64(60)) & np.uint64(1), rat.astype(np.uint64))
+    assert np.array_equal(out >> np.uint64(61), cnt.astype(np.uint64))
+    rows[5, 3] = (8 << 1) | 1                                     # count 8 does not fit
+    assert lib.tip_rows_compact_host(rows.ctypes.data, n, out.ctypes.data) != 0
+    assert b"row 5" in lib.tip_last_error()
+    rows[5, 3] = 2
+    rows[7, 1] = 1 << 20                                          # gene id needs 21 bits
+    assert lib.tip_rows_compact_host(rows.ctypes.data, n, out.ctypes.data) != 0
+    assert lib.tip_rows_compact_host(None, 0, None) == 0
+
+
 def test_sass_is_sm100a_with_fp64_fma_and_cp_async():
     import shutil
     import subprocess

@@ -267,6 +267,20 @@ def test_graph_replay_and_host_entry_equal_stepwise(torch_cuda):
                                     th_h.ctypes.data, p_h.ctypes.data, 6, 0)
     assert rc == 0, lib.tip_last_error()
     assert _relerr(th_h, th_a) < 1e-11 and _relerr(p_h, p_a) < 1e-11
+    # the same entry with 8-byte host rows (TIP_ROWS_COMPACT8), and the device-side expansion on its own
+    rows8 = np.zeros(a.train.n_rows, dtype=np.uint64)
+    assert lib.tip_rows_compact_host(rows.ctypes.data, a.train.n_rows, rows8.ctypes.data) == 0
+    th_c, p_c = np.ascontiguousarray(theta.copy()), np.ascontiguousarray(pr.copy())
+    rc = lib.tip_em_iterations_host(P, K, rows8.ctypes.data, a.train.n_rows, a.train.n_rows_r0, deg.ctypes.data,
+                                    th_c.ctypes.data, p_c.ctypes.data, 6, _cabi.TIP_ROWS_COMPACT8)
+    assert rc == 0, lib.tip_last_error()
+    assert _relerr(th_c, th_a) < 1e-11 and _relerr(p_c, p_a) < 1e-11
+    torch = torch_cuda
+    d8 = torch.from_numpy(rows8.view(np.int64)).to(a.device)
+    d16 = torch.zeros_like(a.train.rows)
+    assert lib.tip_rows_expand(d8.data_ptr(), d16.data_ptr(), a.train.n_rows, 0) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(d16, a.train.rows)                          # bit-exact round trip
 
 
 def test_metrics_kernel_vs_reference_loops(torch_cuda):

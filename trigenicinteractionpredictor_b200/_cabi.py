@@ -21,6 +21,7 @@ TIP_EM_FORCE_GENERIC = 1
 TIP_EM_FP32_COMPUTE = 2
 TIP_EM_WITH_LOGLIK = 4
 TIP_EM_GENE_SEGMENTED = 8
+TIP_ROWS_COMPACT8 = 16
 
 # name -> (restype, argtypes); must list every function include/tip.h declares (tests check this)
 SIGNATURES = {
@@ -43,6 +44,8 @@ SIGNATURES = {
     "tip_metrics": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "tip_em_iterations_host": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int,
                                        c_uint]),
+    "tip_rows_compact_host": (c_int, [c_void_p, c_int64, c_void_p]),
+    "tip_rows_expand": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "tip_ipc_export": (c_int, [c_void_p, c_void_p, _pi64]),
     "tip_ipc_import": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_void_p)]),
     "tip_peer_barrier": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_int, c_int, c_void_p]),

@@ -115,10 +115,12 @@ extern "C" int tip_score(int P, int K, const int32_t *d_g1, const int32_t *d_g2,
 namespace {
 constexpr int kHostChunks = 8;  // row chunks of the first iteration: H2D of chunk i+1 overlaps the E-step of chunk i
 struct HostPool {
-    void *rows = nullptr, *theta = nullptr, *p = nullptr, *stats = nullptr, *deg = nullptr, *ws = nullptr;
-    size_t rows_b = 0, theta_b = 0, p_b = 0, stats_b = 0, deg_b = 0, ws_b = 0;
+    void *rows = nullptr, *rows8 = nullptr, *theta = nullptr, *p = nullptr, *stats = nullptr, *deg = nullptr, *ws = nullptr;
+    size_t rows_b = 0, rows8_b = 0, theta_b = 0, p_b = 0, stats_b = 0, deg_b = 0, ws_b = 0;
     cudaStream_t st = nullptr, copy = nullptr;
     cudaEvent_t ev[kHostChunks] = {};
+    // streamed first iteration: error word on the device and its read-back in pinned host memory
+    unsigned *err = nullptr, *h_err = nullptr;
 };
 HostPool g_pool;
 
@@ -132,7 +134,54 @@ int ensure(void **ptr, size_t *have, size_t need)
     *have = need;
     return 0;
 }
+
+// 8-byte rows (TIP_ROWS_COMPACT8): c | b << 20 | a << 40 | rating << 60 | count << 61  ->  int4 {a, b, c, count << 1 | rating}
+constexpr int kCompactGeneBits = 20;
+constexpr int kCompactMaxCount = 7;
+
+__global__ void rows_expand_kernel(const unsigned long long *__restrict__ in, int4 *__restrict__ out, int64_t n)
+{
+    const unsigned long long mask = (1ull << kCompactGeneBits) - 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long v = in[i];
+        out[i] = make_int4((int)((v >> (2 * kCompactGeneBits)) & mask), (int)((v >> kCompactGeneBits) & mask), (int)(v & mask),
+                           (int)(((v >> 61) << 1) | ((v >> 60) & 1ull)));
+    }
+}
+
+int launch_rows_expand(const void *in8, void *out16, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    const int64_t want = (n + 255) / 256;
+    const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
+    rows_expand_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned long long *>(in8), reinterpret_cast<int4 *>(out16), n);
+    TIP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 }  // namespace
+
+extern "C" int tip_rows_expand(const void *d_rows8, void *d_rows, int64_t n_rows, void *stream)
+{
+    TIP_REQUIRE(n_rows >= 0 && (n_rows == 0 || (d_rows8 && d_rows)), "tip_rows_expand: bad arguments");
+    return launch_rows_expand(d_rows8, d_rows, n_rows, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tip_rows_compact_host(const void *h_rows, int64_t n_rows, uint64_t *h_rows8)
+{
+    TIP_REQUIRE(n_rows >= 0 && (n_rows == 0 || (h_rows && h_rows8)), "tip_rows_compact_host: bad arguments");
+    const int32_t *r = reinterpret_cast<const int32_t *>(h_rows);
+    for (int64_t i = 0; i < n_rows; ++i) {
+        const int32_t a = r[4 * i], b = r[4 * i + 1], c = r[4 * i + 2], w = r[4 * i + 3];
+        TIP_REQUIRE(a >= 0 && b >= 0 && c >= 0 && ((a | b | c) >> kCompactGeneBits) == 0 && w >= 0 && (w >> 1) <= kCompactMaxCount,
+                    "tip_rows_compact_host: row %lld does not fit 8 bytes (gene ids < 2^%d, count <= %d); use the 16-byte rows",
+                    (long long)i, kCompactGeneBits, kCompactMaxCount);
+        h_rows8[i] = (uint64_t)c | ((uint64_t)b << kCompactGeneBits) | ((uint64_t)a << (2 * kCompactGeneBits)) |
+                     ((uint64_t)(w & 1) << 60) | ((uint64_t)(w >> 1) << 61);
+        TIP_REQUIRE(h_rows8[i] != ~0ull, "tip_rows_compact_host: row %lld encodes to the arrival sentinel; use the 16-byte rows",
+                    (long long)i);
+    }
+    return 0;
+}
 
 extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t n_rows, int64_t n_rows_r0,
                                       const int32_t *h_deg, double *h_theta, double *h_p, int n_iter, unsigned flags)
@@ -144,20 +193,59 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
         TIP_CHECK_CUDA(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
         TIP_CHECK_CUDA(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
         for (int c = 0; c < kHostChunks; ++c) TIP_CHECK_CUDA(cudaEventCreateWithFlags(&g.ev[c], cudaEventDisableTiming));
+        TIP_CHECK_CUDA(cudaMalloc(reinterpret_cast<void **>(&g.err), 256));
+        TIP_CHECK_CUDA(cudaMemset(g.err, 0, 256));
+        TIP_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&g.h_err), 64, cudaHostAllocDefault));
+        g.h_err[0] = 0;
     }
     const size_t nth = (size_t)P * K * 8, np = (size_t)2 * K * K * K * 8, nst = (size_t)tip_stats_len(P, K) * 8;
     size_t wsb = 0;
     if (tip_em_workspace_bytes(P, K, n_rows, flags, &wsb) != 0) return -1;
-    int rc;
+    int rc = 0;
+    const bool compact = (flags & TIP_ROWS_COMPACT8) != 0;
+    flags &= ~TIP_ROWS_COMPACT8;
+    const size_t row_b = compact ? 8 : 16;  // bytes per row in the HOST buffer
+    if (compact && (rc = ensure(&g.rows8, &g.rows8_b, (size_t)n_rows * 8))) return rc;
     if ((rc = ensure(&g.rows, &g.rows_b, (size_t)n_rows * 16)) || (rc = ensure(&g.theta, &g.theta_b, nth)) ||
         (rc = ensure(&g.p, &g.p_b, np)) || (rc = ensure(&g.stats, &g.stats_b, nst)) ||
         (rc = ensure(&g.deg, &g.deg_b, (size_t)P * 4)) || (rc = ensure(&g.ws, &g.ws_b, wsb)))
         return rc;
+    const bool tuned = uses_tuned(K, flags);
+    const bool streamed = tuned && n_iter > 0 && n_rows >= 32 * kHostChunks &&
+                          em_streamed_available(K, (flags & TIP_EM_WITH_LOGLIK) != 0, (flags & TIP_EM_FP32_COMPUTE) != 0,
+                                                seg_flag(flags)) && getenv("TIP_HOST_NO_STREAM") == nullptr;
+    char *s_dst = compact ? (char *)g.rows8 : (char *)g.rows;
+    // the small parameter copies are queued FIRST: one host-to-device engine serves every stream in submission order,
+    // and behind the rows they would hold the kernel back until the whole transfer is over (measured)
     TIP_CHECK_CUDA(cudaMemcpyAsync(g.deg, h_deg, (size_t)P * 4, cudaMemcpyHostToDevice, g.st));
     TIP_CHECK_CUDA(cudaMemcpyAsync(g.theta, h_theta, nth, cudaMemcpyHostToDevice, g.st));
     TIP_CHECK_CUDA(cudaMemcpyAsync(g.p, h_p, np, cudaMemcpyHostToDevice, g.st));
+    if (streamed) {
+        // sentinel fill, then ONE copy of all rows; the kernel (launched below, after the fill) follows the DMA front
+        TIP_CHECK_CUDA(cudaMemsetAsync(s_dst, 0xFF, (size_t)n_rows * row_b, g.copy));
+        TIP_CHECK_CUDA(cudaEventRecord(g.ev[0], g.copy));
+        TIP_CHECK_CUDA(cudaMemcpyAsync(s_dst, h_rows, (size_t)n_rows * row_b, cudaMemcpyHostToDevice, g.copy));
+    }
     int it0 = 0;
-    const bool tuned = uses_tuned(K, flags);
+    if (streamed) {
+        // first iteration: ONE launch of the fused kernel consumes the rows as they land (StreamArrive in tip_em.cu)
+        bool handled = false;
+        TIP_CHECK_CUDA(cudaMemsetAsync(g.stats, 0, nst, g.st));
+        rc = launch_em_tuned(P, K, nullptr, 0, 0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
+                             (double *)g.ws, false, false, false, g.st, &handled, 1);
+        if (rc) return rc;
+        TIP_CHECK_CUDA(cudaStreamWaitEvent(g.st, g.ev[0], 0));
+        rc = launch_em_streamed(P, K, s_dst, n_rows, n_rows_r0, (const double *)g.theta, (double *)g.stats, (double *)g.ws,
+                                g.err, compact, g.st);
+        if (rc) return rc;
+        rc = launch_em_tuned(P, K, nullptr, 0, 0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
+                             (double *)g.ws, false, false, false, g.st, &handled, 4);
+        if (rc) return rc;
+        rc = tip_normalise(P, K, (const double *)g.stats, (const int32_t *)g.deg, (double *)g.theta, (double *)g.p, g.st);
+        if (rc) return rc;
+        if (compact && n_iter > 1 && (rc = launch_rows_expand(g.rows8, g.rows, n_rows, g.st))) return rc;
+        it0 = 1;
+    } else
     if (tuned && n_iter > 0 && n_rows >= 32 * kHostChunks) {
         // first iteration: rows arrive in chunks on the copy stream, the fused kernel consumes each chunk as
         // soon as it has landed (statistics accumulate across the chunk launches)
@@ -172,10 +260,13 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
         for (int c = 0; c < kHostChunks; ++c) {
             const int64_t t0 = per * c, t1 = (t0 + per < n_tiles) ? t0 + per : n_tiles;
             if (t0 >= t1) break;
-            TIP_CHECK_CUDA(cudaMemcpyAsync((char *)g.rows + t0 * 512, (const char *)h_rows + t0 * 512, (size_t)(t1 - t0) * 512,
-                                           cudaMemcpyHostToDevice, g.copy));
+            char *dst = compact ? (char *)g.rows8 : (char *)g.rows;
+            TIP_CHECK_CUDA(cudaMemcpyAsync(dst + t0 * 32 * row_b, (const char *)h_rows + t0 * 32 * row_b,
+                                           (size_t)(t1 - t0) * 32 * row_b, cudaMemcpyHostToDevice, g.copy));
             TIP_CHECK_CUDA(cudaEventRecord(g.ev[c], g.copy));
             TIP_CHECK_CUDA(cudaStreamWaitEvent(g.st, g.ev[c], 0));
+            if (compact && (rc = launch_rows_expand((char *)g.rows8 + t0 * 256, (char *)g.rows + t0 * 512, (t1 - t0) * 32, g.st)))
+                return rc;
             int64_t r0 = n_rows_r0 / 32 - t0;
             r0 = r0 < 0 ? 0 : (r0 > t1 - t0 ? t1 - t0 : r0);
             rc = launch_em_tuned(P, K, rows + t0 * 32, (t1 - t0) * 32, r0 * 32, (const double *)g.theta, (const double *)g.p,
@@ -189,7 +280,8 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
         if (rc) return rc;
         it0 = 1;
     } else {
-        TIP_CHECK_CUDA(cudaMemcpyAsync(g.rows, h_rows, (size_t)n_rows * 16, cudaMemcpyHostToDevice, g.st));
+        TIP_CHECK_CUDA(cudaMemcpyAsync(compact ? g.rows8 : g.rows, h_rows, (size_t)n_rows * row_b, cudaMemcpyHostToDevice, g.st));
+        if (compact && (rc = launch_rows_expand(g.rows8, g.rows, n_rows, g.st))) return rc;
     }
     for (int it = it0; it < n_iter; ++it) {
         rc = tip_em_step(P, K, g.rows, n_rows, n_rows_r0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
@@ -200,7 +292,21 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
     }
     TIP_CHECK_CUDA(cudaMemcpyAsync(h_theta, g.theta, nth, cudaMemcpyDeviceToHost, g.st));
     TIP_CHECK_CUDA(cudaMemcpyAsync(h_p, g.p, np, cudaMemcpyDeviceToHost, g.st));
+    if (streamed) TIP_CHECK_CUDA(cudaMemcpyAsync(g.h_err, g.err, sizeof(unsigned), cudaMemcpyDeviceToHost, g.st));
     TIP_CHECK_CUDA(cudaStreamSynchronize(g.st));
+    if (streamed && getenv("TIP_HOST_STREAM_DEBUG")) {
+        unsigned long long d[5];
+        TIP_CHECK_CUDA(cudaMemcpy(d, reinterpret_cast<unsigned long long *>(g.err) + 8, sizeof(d), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "stream dbg: first rows +%.1f us, last rows +%.1f us, end +%.1f us, spins %llu\n", (d[1] - d[0]) * 1e-3,
+                (d[2] - d[0]) * 1e-3, (d[3] - d[0]) * 1e-3, d[4]);
+    }
+    if (streamed && g.h_err[0] != 0) {
+        TIP_CHECK_CUDA(cudaStreamSynchronize(g.copy));
+        TIP_CHECK_CUDA(cudaMemset(g.err, 0, sizeof(unsigned)));
+        g.h_err[0] = 0;
+        set_error("tip_em_iterations_host: the rows did not arrive on the device within 5 s (copy stream stalled)");
+        return -3;
+    }
     return 0;
 }
 

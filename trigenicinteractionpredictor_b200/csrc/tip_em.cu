@@ -181,11 +181,34 @@ struct ScatterMap {
 // d = eps + sum_b th_b[b] y[b].  Lanes read Z of their own slot-a gene through L1 (one address per run of equal
 // gene, so a warp instruction touches one or two lines).  The kernel is then bound by the theta gather and the
 // slot-b/c reductions, not by the FMA pipe; bench.py reports it separately from the headline kernel.
-template <int K, int NBUF, int MINB, bool LL, typename T, bool SEG>
+//
+// STREAM = true (host-buffer entry, tip_em_iterations_host): the rows are still arriving from the host while the
+// kernel runs.  The device buffer is filled with a sentinel (all ones, never a valid row) before ONE host-to-device
+// copy of all rows is queued on a copy stream; a warp polls the rows of its next tile (ld.cv) until none of them is
+// the sentinel.  Rows are written once, so an 8-byte word that is not the sentinel is final: no flags, no chunking,
+// one launch and one copy, and the kernel follows the DMA front tile by tile.  sa.compact: the rows are the 8-byte
+// host format (tip_rows_compact_host), decoded on load.  A warp that waits longer than sa.timeout_ns sets *sa.err and
+// treats every later row as padding (count 0), so a stalled host cannot hang the GPU.
+struct StreamArrive {
+    unsigned *err;
+    int compact;
+    unsigned long long timeout_ns;
+    unsigned long long *dbg;  // optional (TIP_HOST_STREAM_DEBUG): CTA 0 records {start, first rows, last rows, end, spins}
+};
+constexpr unsigned long long kRowSentinel = ~0ull;
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int K, int NBUF, int MINB, bool LL, typename T, bool SEG, bool STREAM = false>
 __global__ void __launch_bounds__(32, MINB)
     em_fused_kernel(int P, const int4 *__restrict__ rows, int n_tiles, int n_tiles_r0, const double *__restrict__ theta,
                     int p_off0, int p_off1, double *__restrict__ stats, double *__restrict__ Mg,
-                    const double *__restrict__ Zg, int red_scatter)
+                    const double *__restrict__ Zg, int red_scatter, StreamArrive sa)
 {
     using C = EmCfg<K, NBUF>;
     constexpr int KP = C::KP, RS = C::RS, K3 = C::K3, CB = C::CB, RC = C::RC, CA = C::CA;
@@ -210,6 +233,58 @@ __global__ void __launch_bounds__(32, MINB)
     asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(gx_v));
     const int4 *rp = rows + (int64_t)bx_v * 32 + lane;  // next tile of rows this lane will fetch
     const int64_t rstride = (int64_t)gx_v * 32;
+    // STREAM: per-lane tile index of the next fetch
+    unsigned tile_v = bx_v;
+    bool stream_dead = false;
+    unsigned long long dbg_spins = 0;
+    if constexpr (STREAM) {
+        if (sa.dbg != nullptr && bx_v == 0 && lane == 0) sa.dbg[0] = global_timer_ns();
+    }
+    auto next_rows = [&]() -> int4 {
+        int4 v;
+        if constexpr (STREAM) {
+            const unsigned long long *src =
+                sa.compact ? reinterpret_cast<const unsigned long long *>(rows) + (int64_t)tile_v * 32 + lane
+                           : reinterpret_cast<const unsigned long long *>(rp);
+            unsigned long long q0 = 0, q1 = 0, t_start = 0;
+            unsigned spins = 0;
+            for (;;) {
+                if (!stream_dead) {
+                    q0 = __ldcv(src);
+                    q1 = sa.compact ? 0ull : __ldcv(src + 1);
+                }
+                const bool ok = stream_dead || (q0 != kRowSentinel && q1 != kRowSentinel);
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (spins == 0) t_start = global_timer_ns();
+                __nanosleep(100);
+                if ((++spins & 255u) == 0 && global_timer_ns() - t_start > sa.timeout_ns) {
+                    stream_dead = true;
+                    *sa.err = 1u;
+                }
+            }
+            stream_dead = __any_sync(0xffffffffu, stream_dead);
+            if (sa.dbg != nullptr && bx_v == 0 && lane == 0) {
+                dbg_spins += spins;
+                if (tile_v == 0) sa.dbg[1] = global_timer_ns();
+                sa.dbg[2] = global_timer_ns();
+                sa.dbg[4] = dbg_spins;
+            }
+            if (stream_dead) {
+                v = make_int4(0, 0, 0, 0);
+            } else if (sa.compact) {
+                const unsigned long long mask = (1ull << 20) - 1;
+                v = make_int4((int)((q0 >> 40) & mask), (int)((q0 >> 20) & mask), (int)(q0 & mask),
+                              (int)(((q0 >> 61) << 1) | ((q0 >> 60) & 1ull)));
+            } else {
+                v = make_int4((int)(unsigned)q0, (int)(q0 >> 32), (int)(unsigned)q1, (int)(q1 >> 32));
+            }
+            tile_v += gx_v;
+        } else {
+            v = *rp;
+        }
+        rp += rstride;
+        return v;
+    };
 
     // phase B lane mapping
     const int b_lane = lane % K;
@@ -251,18 +326,13 @@ __global__ void __launch_bounds__(32, MINB)
     // ---- software pipeline prologue (NBUF == 2: rows of the next tile are gathered one tile ahead) ----
     int4 ids_next = make_int4(0, 0, 0, 0);
     if (NBUF == 2 && w0 < n_tiles) {
-        ids_sm[lane] = *rp;
-        rp += rstride;
+        ids_sm[lane] = next_rows();
         __syncwarp();
         gather_tile<K, RS, KP>(theta, ids_sm, stage0, lane);
         cp_async_commit();
-        if (w0 + W < n_tiles) {
-            ids_next = *rp;
-            rp += rstride;
-        }
+        if (w0 + W < n_tiles) ids_next = next_rows();
     } else if (NBUF == 1 && w0 < n_tiles) {
-        ids_next = *rp;
-        rp += rstride;
+        ids_next = next_rows();
     }
 
     int buf = 0;
@@ -276,10 +346,7 @@ __global__ void __launch_bounds__(32, MINB)
                 __syncwarp();
                 gather_tile<K, RS, KP>(theta, ids_sm + (buf ^ 1) * 32, stage0 + (buf ^ 1) * 32 * RS, lane);
                 cp_async_commit();
-                if (t + 2 * W < n_tiles) {
-                    ids_next = *rp;
-                    rp += rstride;
-                }
+                if (t + 2 * W < n_tiles) ids_next = next_rows();
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
@@ -289,10 +356,7 @@ __global__ void __launch_bounds__(32, MINB)
             __syncwarp();
             gather_tile<K, RS, KP>(theta, ids_sm, stage0, lane);
             cp_async_commit();
-            if (t + W < n_tiles) {
-                ids_next = *rp;
-                rp += rstride;
-            }
+            if (t + W < n_tiles) ids_next = next_rows();
             cp_async_wait<0>();
         }
         __syncwarp();
@@ -557,6 +621,9 @@ __global__ void __launch_bounds__(32, MINB)
         ll = warp_sum(ll);
         if (lane == 0 && ll != 0.0) red_add_f64(stats + stats_off_ll(P, K), ll);
     }
+    if constexpr (STREAM) {
+        if (sa.dbg != nullptr && bx_v == 0 && lane == 0) sa.dbg[3] = global_timer_ns();
+    }
 }
 
 // Z[r][g][bc] = sum_a theta[g][a] * p[a][bc][r]   (TIP_EM_GENE_SEGMENTED; 2*P*K^3 FMA per iteration in total)
@@ -801,19 +868,20 @@ static int em_red_scatter()
     return v;
 }
 
-template <int K, int NBUF, int MINB, bool LL, typename T = double, bool SEG = false>
+template <int K, int NBUF, int MINB, bool LL, typename T = double, bool SEG = false, bool STREAM = false>
 static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, int p_off0,
-                          int p_off1, double *stats, double *Mg, cudaStream_t st)
+                          int p_off1, double *stats, double *Mg, cudaStream_t st, StreamArrive sa = StreamArrive{})
 {
     using C = EmCfg<K, NBUF>;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL, T, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)C::SMEM));
-        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL, T, SEG>,
+        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL, T, SEG, STREAM>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        TIP_CHECK_CUDA(cudaFuncSetAttribute(em_fused_kernel<K, NBUF, MINB, LL, T, SEG, STREAM>,
                                             cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         int nb = 0;
-        TIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, em_fused_kernel<K, NBUF, MINB, LL, T, SEG>, 32, C::SMEM));
+        TIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, em_fused_kernel<K, NBUF, MINB, LL, T, SEG, STREAM>, 32,
+                                                                     C::SMEM));
         TIP_REQUIRE(nb >= 1, "em_fused_kernel<%d> does not fit on an SM (smem %zu)", K, C::SMEM);
         blocks_per_sm = nb;
     }
@@ -822,9 +890,9 @@ static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_row
     int64_t cap = (int64_t)sm_count() * blocks_per_sm;
     int grid = (int)(n_tiles < cap ? n_tiles : cap);
     if (grid < 1) grid = 1;
-    em_fused_kernel<K, NBUF, MINB, LL, T, SEG><<<grid, 32, C::SMEM, st>>>(
+    em_fused_kernel<K, NBUF, MINB, LL, T, SEG, STREAM><<<grid, 32, C::SMEM, st>>>(
         P, rows, (int)n_tiles, (int)(n_rows_r0 / 32), theta, p_off0, p_off1, stats, Mg,
-        SEG ? Mg + 2 * (size_t)P * K * K : nullptr, em_red_scatter());
+        SEG ? Mg + 2 * (size_t)P * K * K : nullptr, em_red_scatter(), sa);
     TIP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1188,6 +1256,41 @@ int launch_loglik_seg(int P, int K, const int4 *rows, int64_t n_rows, const doub
     loglik_seg_kernel<<<grid, 32, smem, st>>>(P, K, rows, (int)n_tiles, theta, Zws, partials, counter, out);
     TIP_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+// The "run" phase of the plain fp64 K <= 10 E-step over rows that are still arriving from the host (see StreamArrive).
+// Between launch_em_tuned(phases = kPhaseBegin) and (phases = kPhaseEnd) on the same stream.
+bool em_streamed_available(int K, bool with_ll, bool f32, bool seg) { return K >= 1 && K <= 10 && !with_ll && !f32 && !seg; }
+
+template <int K>
+static int launch_streamed_k(int P, const void *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, double *stats,
+                             double *ws, StreamArrive sa, cudaStream_t st)
+{
+    return launch_variant<K, 1, 12, false, double, false, true>(P, reinterpret_cast<const int4 *>(rows), n_rows, n_rows_r0, theta,
+                                                                g_phase_off0, g_phase_off1, stats, ws, st, sa);
+}
+
+int launch_em_streamed(int P, int K, const void *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, double *stats,
+                       double *ws, unsigned *err, bool compact, cudaStream_t st)
+{
+    StreamArrive sa;
+    sa.dbg = getenv("TIP_HOST_STREAM_DEBUG") ? reinterpret_cast<unsigned long long *>(err) + 8 : nullptr;
+    sa.err = err;
+    sa.compact = compact ? 1 : 0;
+    sa.timeout_ns = 5000000000ull;  // 5 s: a host that stopped feeding the copy stream must not hang the GPU
+    switch (K) {
+        case 1: return launch_streamed_k<1>(P, rows, n_rows, n_rows_r0, theta, stats, ws, sa, st);
+        case 2: return launch_streamed_k<2>(P, rows, n_rows, n_rows_r0, theta, stats, ws, sa, st);
+        case 3: return launch_streamed_k<3>(P, rows, n_rows, n_rows_r0, theta, stats, ws, sa, st);
+        case 4: return launch_streamed_k<4>(P, rows, n_rows, n_rows_r0, theta, stats, ws, sa, st);
+        case 5: return launch_streamed_k<5>(P, rows, n_rows, n_rows_r0, theta, stats, ws, sa, st);
+        case 6: return launch_streamed_k<6>(P, rows, n_rows, n_rows_r0, theta, stats, ws, sa, st);
+        case 7: return launch_streamed_k<7>(P, rows, n_rows, n_rows_r0, theta, stats, ws, sa, st);
+        case 8: return launch_streamed_k<8>(P, rows, n_rows, n_rows_r0, theta, stats, ws, sa, st);
+        case 9: return launch_streamed_k<9>(P, rows, n_rows, n_rows_r0, theta, stats, ws, sa, st);
+        case 10: return launch_streamed_k<10>(P, rows, n_rows, n_rows_r0, theta, stats, ws, sa, st);
+        default: set_error("launch_em_streamed: K = %d has no streamed kernel", K); return -1;
+    }
 }
 
 int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta,
