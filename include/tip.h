@@ -119,6 +119,16 @@ int tip_metrics_workspace_bytes(int64_t T, size_t *bytes);
 int tip_metrics(const double *d_scores, const int32_t *d_labels, int64_t T, int64_t positives_number,
                 void *d_ws, size_t ws_bytes, int64_t *d_out, void *stream);
 
+/* ---- testResultsReducer.py:160-184: mean / median / standard deviation of every test triplet across samples ----
+ * d_scores[S][T]: score of triplet t in sample j at [j * T + t]; d_n[t] (or NULL = S) = how many leading samples of
+ * triplet t are valid.  mean = sequential sum in sample order / n; median = the reference's rule (ascending sort;
+ * odd n: element round-half-even(n / 2), even n: mean of the two centre elements); std = sqrt(sum over the sorted
+ * values of (x - mean)^2 / n).  Every operation is a separately rounded IEEE operation in the reference's order, so
+ * mean and median are bit-identical to CPython.  d_sorted[S][T]: scratch, returns the ascending values per triplet.
+ * The AUC / precision / recall / fallout of the mean scores then come from tip_metrics. */
+int tip_reduce_samples(int S, int64_t T, const double *d_scores, const int32_t *d_n, double *d_sorted, double *d_mean,
+                       double *d_median, double *d_std, void *stream);
+
 /* ---- host-buffer entry: n_iter full make_iteration()s with HOST inputs and outputs ----
  * Copies rows/deg/theta/p to the device, runs n_iter x (E-step, M-step), copies theta/p back and
  * synchronises.  Allocates and frees its own device memory (the only function that does).
