@@ -449,21 +449,15 @@ def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
                 if rc != 0:
                     raise RuntimeError(lib.tip_last_error())
             return step
-        rows8_d = torch.empty(max(n_rows, 1), dtype=torch.int64, device=dev) if compact else None
+        src = rows8_h if compact else rows_h
 
         def step():
-            if compact:
-                rows8_d.copy_(rows8_h, non_blocking=True)
-                rc = lib.tip_rows_expand(rows8_d.data_ptr(), eng.train.rows.data_ptr(), n_rows,
-                                         torch.cuda.current_stream(dev).cuda_stream)
-                if rc != 0:
-                    raise RuntimeError(lib.tip_last_error())
-            else:
-                eng.train.rows.copy_(rows_h, non_blocking=True)
+            # small parameter copies first (the H2D engine is FIFO across streams), then the E-step follows the rows'
+            # DMA front (tip_em_step_host_rows), statistics exchange, M-step
             eng.train.deg.copy_(deg_h, non_blocking=True)
             eng.theta.copy_(th_h.view(-1), non_blocking=True)
             eng.p.copy_(p_h.view(-1), non_blocking=True)
-            eng.em_iteration()
+            eng.em_iteration_host_rows(src, compact)
             th_h.view(-1).copy_(eng.theta, non_blocking=True)
             p_h.view(-1).copy_(eng.p, non_blocking=True)
             torch.cuda.synchronize(dev)
@@ -485,8 +479,10 @@ def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
     if world == 1:
         api = "tip_em_iterations_host (C ABI, pinned host buffers, 8-byte rows: TIP_ROWS_COMPACT8)"
     else:
-        api = ("EMEngine.em_iteration with pinned host copies, 8-byte rows + tip_rows_expand (link-sharded, %s exchange)"
-               % args.exchange)
+        api = ("EMEngine.em_iteration_host_rows: pinned host buffers, 8-byte rows, tip_em_step_host_rows follows the DMA "
+               "front (link-sharded, %s exchange)" % args.exchange)
+        if not eng.host_rows_arrived():
+            raise RuntimeError("streamed E-step timed out waiting for its rows")
     return {"value": L_total * steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(n_rows * 8 + fixed),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / steps, "api": api,
             "rows16": {"value": L_total * steps / dt16, "ms_per_step": 1e3 * dt16 / steps,

@@ -88,6 +88,19 @@ int tip_em_workspace_bytes(int P, int K, int64_t n_rows, unsigned flags, size_t 
 int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int64_t n_rows_r0, const double *d_theta,
                 const double *d_p, double *d_stats, void *d_ws, size_t ws_bytes, unsigned flags, void *stream);
 
+/* ---- E-step over rows that are still in HOST memory (the same statistics as tip_em_step) ----
+ * h_rows: pinned host rows, 16 bytes each (row_flags = 0) or 8 bytes each (row_flags = TIP_ROWS_COMPACT8).
+ * d_rows_dev: n_rows * 16 (or * 8) bytes of device memory that receives them.  The function fills d_rows_dev with a
+ * sentinel and queues ONE host-to-device copy on `copy_stream`; the fused kernel, launched on `stream`, polls the
+ * rows of each tile until they have landed, so the E-step follows the DMA front instead of waiting for the copy
+ * (one launch, no chunking).  Queue small parameter copies BEFORE this call: the host-to-device engine serves all
+ * streams in submission order.  d_err: 4 bytes of device memory, zero on entry; set to 1 when a tile waited more
+ * than 5 s (the statistics are then incomplete).  Plain fp64 kernels for K <= 10 only (-1 otherwise: copy the rows
+ * and call tip_em_step).  `stream` and `copy_stream` must differ.  Not capturable in a CUDA graph. */
+int tip_em_step_host_rows(int P, int K, const void *h_rows, int64_t n_rows, int64_t n_rows_r0, unsigned row_flags,
+                          void *d_rows_dev, const double *d_theta, const double *d_p, double *d_stats, void *d_ws,
+                          size_t ws_bytes, unsigned *d_err, void *stream, void *copy_stream);
+
 /* ---- Model.make_iteration, M-step half (TIP.py:1016-1043) ----
  * theta[g][k] = Ntheta[g][k] / deg[g];  npr = p*S;  p = npr / (eps + npr0 + npr1).  In place on d_p.
  * Genes with deg == 0 produce inf/nan like a float division would; the Python Model raises

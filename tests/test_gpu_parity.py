@@ -283,6 +283,50 @@ def test_graph_replay_and_host_entry_equal_stepwise(torch_cuda):
     assert torch.equal(d16, a.train.rows)                          # bit-exact round trip
 
 
+def test_em_step_host_rows_equals_em_step(torch_cuda):
+    """The streamed E-step (rows polled as the host-to-device copy lands) gives the statistics of tip_em_step, for both
+    host row formats, also when calls follow each other without a synchronisation in between."""
+    torch = torch_cuda
+    from trigenicinteractionpredictor_b200 import _cabi
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    lib = _cabi.load()
+    for K, L in ((10, 50000), (4, 20000), (7, 20000)):
+        P = 500
+        g, n0, n1, theta, pr = _random_problem(P, L, K, 300 + K)
+        eng = EMEngine(P, K)
+        eng.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+        eng.set_params(theta, pr)
+        eng.em_step()
+        ref = eng.stats.clone()
+        rows_h = eng.train.rows.cpu().pin_memory()
+        rows8_h = torch.empty(eng.train.n_rows, dtype=torch.int64).pin_memory()
+        assert lib.tip_rows_compact_host(rows_h.data_ptr(), eng.train.n_rows, rows8_h.data_ptr()) == 0
+        for compact, src in ((False, rows_h), (True, rows8_h)):
+            outs = [torch.zeros_like(ref) for _ in range(3)]
+            for o in outs:                                       # back to back: the copy stream must wait for the reader
+                eng.em_step_host_rows(src, compact, o)
+            torch.cuda.synchronize()
+            assert eng.host_rows_arrived()
+            for o in outs:
+                assert _relerr(o.cpu().numpy(), ref.cpu().numpy()) < 1e-11     # (0 against 0 counts as equal)
+        # whole iterations through the host-rows path equal the resident path
+        a = EMEngine(P, K)
+        a.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+        a.set_params(theta, pr)
+        for _ in range(3):
+            eng.em_iteration_host_rows(rows8_h, True)
+            a.em_iteration()
+        th_e, p_e = eng.get_params()
+        th_a, p_a = a.get_params()
+        assert _relerr(th_e, th_a) < 1e-11 and _relerr(p_e, p_a) < 1e-11
+    big = EMEngine(300, 12)
+    g, n0, n1, theta, pr = _random_problem(300, 2000, 12, 5)
+    big.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+    big.set_params(theta, pr)
+    with pytest.raises(_cabi.TipLibraryError):                   # no streamed kernel for K > 10: refuses, no fallback
+        big.em_step_host_rows(big.train.rows.cpu().pin_memory(), False)
+
+
 def test_metrics_kernel_vs_reference_loops(torch_cuda):
     torch = torch_cuda
     from oracle import mmsbm_oracle as orc

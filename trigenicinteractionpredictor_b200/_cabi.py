@@ -35,6 +35,8 @@ SIGNATURES = {
     "tip_em_workspace_bytes": (c_int, [c_int, c_int, c_int64, c_uint, _psz]),
     "tip_em_step": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                             c_uint, c_void_p]),
+    "tip_em_step_host_rows": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_uint, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "tip_normalise": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tip_loglik_workspace_bytes": (c_size_t, [c_int, c_int]),
     "tip_loglik": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_uint,

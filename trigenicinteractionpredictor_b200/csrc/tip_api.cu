@@ -77,6 +77,49 @@ extern "C" int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int
     return launch_em_generic(P, K, rows, n_rows, n_rows_r0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws), st);
 }
 
+extern "C" int tip_em_step_host_rows(int P, int K, const void *h_rows, int64_t n_rows, int64_t n_rows_r0, unsigned row_flags,
+                                     void *d_rows_dev, const double *d_theta, const double *d_p, double *d_stats, void *d_ws,
+                                     size_t ws_bytes, unsigned *d_err, void *stream, void *copy_stream)
+{
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream), cs = reinterpret_cast<cudaStream_t>(copy_stream);
+    TIP_REQUIRE(P > 0 && valid_K(K) && em_streamed_available(K, false, false, false),
+                "tip_em_step_host_rows: the streamed E-step exists for the plain fp64 K <= 10 kernels (got K=%d); copy the "
+                "rows and call tip_em_step", K);
+    TIP_REQUIRE(n_rows > 0 && n_rows % 32 == 0 && n_rows_r0 >= 0 && n_rows_r0 <= n_rows && n_rows_r0 % 32 == 0,
+                "tip_em_step_host_rows: n_rows (%lld) and n_rows_r0 (%lld) must be multiples of 32 from tip_pack_rows",
+                (long long)n_rows, (long long)n_rows_r0);
+    TIP_REQUIRE(h_rows && d_rows_dev && d_theta && d_p && d_stats && d_err && cs != st && (row_flags & ~TIP_ROWS_COMPACT8) == 0,
+                "tip_em_step_host_rows: bad arguments (two distinct streams are required)");
+    const size_t need = em_tuned_workspace_bytes(P, K, false);
+    TIP_REQUIRE(need == 0 || (d_ws != nullptr && ws_bytes >= need),
+                "tip_em_step_host_rows: K=%d needs %zu bytes of workspace (got %zu), see tip_em_workspace_bytes", K, need, ws_bytes);
+    static cudaEvent_t ev_free = nullptr, ev_filled = nullptr;
+    if (!ev_free) {
+        TIP_CHECK_CUDA(cudaEventCreateWithFlags(&ev_free, cudaEventDisableTiming));
+        TIP_CHECK_CUDA(cudaEventCreateWithFlags(&ev_filled, cudaEventDisableTiming));
+    }
+    const bool compact = (row_flags & TIP_ROWS_COMPACT8) != 0;
+    const size_t bytes = (size_t)n_rows * (compact ? 8 : 16);
+    // the copy stream may not touch d_rows_dev before everything already queued on `stream` (an earlier E-step that
+    // reads it) is done; then: sentinel fill, ONE copy of all rows, and the kernel starts as soon as the fill is over
+    TIP_CHECK_CUDA(cudaEventRecord(ev_free, st));
+    TIP_CHECK_CUDA(cudaStreamWaitEvent(cs, ev_free, 0));
+    TIP_CHECK_CUDA(cudaMemsetAsync(d_rows_dev, 0xFF, bytes, cs));
+    TIP_CHECK_CUDA(cudaEventRecord(ev_filled, cs));
+    TIP_CHECK_CUDA(cudaMemcpyAsync(d_rows_dev, h_rows, bytes, cudaMemcpyHostToDevice, cs));
+    TIP_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * (size_t)tip_stats_len(P, K), st));
+    bool handled = false;
+    int rc = launch_em_tuned(P, K, nullptr, 0, 0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws), false, false, false,
+                             st, &handled, 1);
+    if (rc) return rc;
+    TIP_CHECK_CUDA(cudaStreamWaitEvent(st, ev_filled, 0));
+    rc = launch_em_streamed(P, K, d_rows_dev, n_rows, n_rows_r0, d_theta, d_stats, reinterpret_cast<double *>(d_ws), d_err,
+                            compact, st);
+    if (rc) return rc;
+    return launch_em_tuned(P, K, nullptr, 0, 0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws), false, false, false, st,
+                           &handled, 4);
+}
+
 extern "C" int tip_normalise(int P, int K, const double *d_stats, const int32_t *d_deg, double *d_theta, double *d_p,
                              void *stream)
 {

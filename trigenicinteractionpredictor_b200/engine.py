@@ -141,6 +141,51 @@ class EMEngine:
                                          self.flags, self._stream()), "tip_em_step")
         self.launches += 3 if (self.K > 4 and not (self.flags & _cabi.TIP_EM_FORCE_GENERIC)) else 2
 
+    def em_step_host_rows(self, h_rows: torch.Tensor, compact: bool, stats=None):
+        """E-step of this rank's rows read from PINNED HOST memory (16-byte rows, or the 8-byte rows of
+        tip_rows_compact_host): one copy on a side stream, the fused kernel follows the DMA front
+        (tip_em_step_host_rows).  K <= 10, default flags."""
+        t = self.train
+        stats = self.stats if stats is None else stats
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._stream_err = torch.zeros(64, dtype=torch.int32, device=self.device)
+            self._rows_dev = None
+        need = t.n_rows * (8 if compact else 16)
+        if self._rows_dev is None or self._rows_dev.numel() < need:
+            self._rows_dev = torch.empty(need, dtype=torch.uint8, device=self.device)
+        _cabi.check(self.lib.tip_em_step_host_rows(
+            self.P, self.K, ctypes.c_void_p(h_rows.data_ptr()), t.n_rows, t.n_rows_r0,
+            _cabi.TIP_ROWS_COMPACT8 if compact else 0, _ptr(self._rows_dev), _ptr(self.theta), _ptr(self.p), _ptr(stats),
+            _ptr(self.em_ws), self.em_ws_bytes, _ptr(self._stream_err), self._stream(),
+            ctypes.c_void_p(self._copy_stream.cuda_stream)), "tip_em_step_host_rows")
+        self.launches += 3 if self.K > 4 else 2
+
+    def host_rows_arrived(self) -> bool:
+        """False when a streamed E-step gave up waiting for its rows (synchronises)."""
+        bad = int(self._stream_err[0].item()) != 0
+        if bad:
+            self._stream_err.zero_()
+        return not bad
+
+    def em_iteration_host_rows(self, h_rows: torch.Tensor, compact: bool):
+        """em_iteration() with the E-step reading its rows from pinned host memory."""
+        if self.peer is not None:
+            par = self._iter & 1
+            self._iter += 1
+            self.em_step_host_rows(h_rows, compact, self.peer.stats(par))
+            _cabi.check(self.lib.tip_peer_barrier(self.peer.flag_ptrs, _ptr(self.peer.epoch), self.peer.rank,
+                                                  self.peer.world, self._stream()), "tip_peer_barrier")
+            _cabi.check(self.lib.tip_normalise_peers(self.P, self.K, self.peer.stats_ptrs[par], self.peer.world,
+                                                     _ptr(self.train.deg), _ptr(self.theta), _ptr(self.p),
+                                                     self._stream()), "tip_normalise_peers")
+            self.launches += 2
+            return
+        self.em_step_host_rows(h_rows, compact)
+        if self.world > 1:
+            _dist.allreduce_sum_(self.stats, self.group)
+        self.normalise()
+
     def normalise(self):
         _cabi.check(self.lib.tip_normalise(self.P, self.K, _ptr(self.stats), _ptr(self.train.deg), _ptr(self.theta),
                                            _ptr(self.p), self._stream()), "tip_normalise")
