@@ -79,11 +79,11 @@ def test_reducer_reproduces_reference_files(torch_cuda, tmp_path):
 
 
 @pytest.mark.gpu
-def test_reduce_samples_kernel_vs_oracle_ragged(torch_cuda):
+@pytest.mark.parametrize("T,S", [(4000, 13), (1500, 64), (300, 200)])     # 200 samples: the global-scratch sort path
+def test_reduce_samples_kernel_vs_oracle_ragged(torch_cuda, T, S):
     from oracle import reducer_oracle as ro
     from trigenicinteractionpredictor_b200 import testResultsReducer as trr
     rng = np.random.default_rng(9)
-    T, S = 4000, 13
     cols, labs = [], []
     for t in range(T):
         n = 1 + (t % S)

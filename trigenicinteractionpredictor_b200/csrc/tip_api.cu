@@ -236,10 +236,11 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
         TIP_CHECK_CUDA(cudaStreamCreateWithFlags(&g.st, cudaStreamNonBlocking));
         TIP_CHECK_CUDA(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
         for (int c = 0; c < kHostChunks; ++c) TIP_CHECK_CUDA(cudaEventCreateWithFlags(&g.ev[c], cudaEventDisableTiming));
-        TIP_CHECK_CUDA(cudaMalloc(reinterpret_cast<void **>(&g.err), 256));
-        TIP_CHECK_CUDA(cudaMemset(g.err, 0, 256));
-        TIP_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&g.h_err), 64, cudaHostAllocDefault));
-        g.h_err[0] = 0;
+        // the error word of the streamed kernel lives in mapped pinned host memory: written (only on a timeout)
+        // straight from the kernel, read by the host after the synchronisation - no device-to-host copy per call
+        TIP_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&g.h_err), 256, cudaHostAllocMapped));
+        memset(g.h_err, 0, 256);
+        TIP_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&g.err), g.h_err, 0));
     }
     const size_t nth = (size_t)P * K * 8, np = (size_t)2 * K * K * K * 8, nst = (size_t)tip_stats_len(P, K) * 8;
     size_t wsb = 0;
@@ -260,14 +261,17 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
     char *s_dst = compact ? (char *)g.rows8 : (char *)g.rows;
     // the small parameter copies are queued FIRST: one host-to-device engine serves every stream in submission order,
     // and behind the rows they would hold the kernel back until the whole transfer is over (measured)
-    TIP_CHECK_CUDA(cudaMemcpyAsync(g.deg, h_deg, (size_t)P * 4, cudaMemcpyHostToDevice, g.st));
     TIP_CHECK_CUDA(cudaMemcpyAsync(g.theta, h_theta, nth, cudaMemcpyHostToDevice, g.st));
     TIP_CHECK_CUDA(cudaMemcpyAsync(g.p, h_p, np, cudaMemcpyHostToDevice, g.st));
+    if (!streamed) TIP_CHECK_CUDA(cudaMemcpyAsync(g.deg, h_deg, (size_t)P * 4, cudaMemcpyHostToDevice, g.st));
     if (streamed) {
         // sentinel fill, then ONE copy of all rows; the kernel (launched below, after the fill) follows the DMA front
         TIP_CHECK_CUDA(cudaMemsetAsync(s_dst, 0xFF, (size_t)n_rows * row_b, g.copy));
         TIP_CHECK_CUDA(cudaEventRecord(g.ev[0], g.copy));
         TIP_CHECK_CUDA(cudaMemcpyAsync(s_dst, h_rows, (size_t)n_rows * row_b, cudaMemcpyHostToDevice, g.copy));
+        // only the M-step needs the degrees: their copy goes behind the rows, off the kernel's critical path
+        TIP_CHECK_CUDA(cudaMemcpyAsync(g.deg, h_deg, (size_t)P * 4, cudaMemcpyHostToDevice, g.copy));
+        TIP_CHECK_CUDA(cudaEventRecord(g.ev[1], g.copy));
     }
     int it0 = 0;
     if (streamed) {
@@ -284,6 +288,7 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
         rc = launch_em_tuned(P, K, nullptr, 0, 0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
                              (double *)g.ws, false, false, false, g.st, &handled, 4);
         if (rc) return rc;
+        TIP_CHECK_CUDA(cudaStreamWaitEvent(g.st, g.ev[1], 0));
         rc = tip_normalise(P, K, (const double *)g.stats, (const int32_t *)g.deg, (double *)g.theta, (double *)g.p, g.st);
         if (rc) return rc;
         if (compact && n_iter > 1 && (rc = launch_rows_expand(g.rows8, g.rows, n_rows, g.st))) return rc;
@@ -335,17 +340,15 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
     }
     TIP_CHECK_CUDA(cudaMemcpyAsync(h_theta, g.theta, nth, cudaMemcpyDeviceToHost, g.st));
     TIP_CHECK_CUDA(cudaMemcpyAsync(h_p, g.p, np, cudaMemcpyDeviceToHost, g.st));
-    if (streamed) TIP_CHECK_CUDA(cudaMemcpyAsync(g.h_err, g.err, sizeof(unsigned), cudaMemcpyDeviceToHost, g.st));
     TIP_CHECK_CUDA(cudaStreamSynchronize(g.st));
     if (streamed && getenv("TIP_HOST_STREAM_DEBUG")) {
         unsigned long long d[5];
-        TIP_CHECK_CUDA(cudaMemcpy(d, reinterpret_cast<unsigned long long *>(g.err) + 8, sizeof(d), cudaMemcpyDeviceToHost));
+        memcpy(d, reinterpret_cast<unsigned long long *>(g.h_err) + 8, sizeof(d));
         fprintf(stderr, "stream dbg: first rows +%.1f us, last rows +%.1f us, end +%.1f us, spins %llu\n", (d[1] - d[0]) * 1e-3,
                 (d[2] - d[0]) * 1e-3, (d[3] - d[0]) * 1e-3, d[4]);
     }
     if (streamed && g.h_err[0] != 0) {
         TIP_CHECK_CUDA(cudaStreamSynchronize(g.copy));
-        TIP_CHECK_CUDA(cudaMemset(g.err, 0, sizeof(unsigned)));
         g.h_err[0] = 0;
         set_error("tip_em_iterations_host: the rows did not arrive on the device within 5 s (copy stream stalled)");
         return -3;

@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(32, MINB)
     asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(gx_v));
     const int4 *rp = rows + (int64_t)bx_v * 32 + lane;  // next tile of rows this lane will fetch
     const int64_t rstride = (int64_t)gx_v * 32;
+    // (Tried: staggering the start of the co-resident warp-CTAs of an SM by 0.3-5 us each, in case the 12 warps run
+    // their phases in lockstep - no effect at 800 k or 10 M links, so the phases already interleave.)
     // STREAM: per-lane tile index of the next fetch
     unsigned tile_v = bx_v;
     bool stream_dead = false;
@@ -648,20 +650,20 @@ __global__ void seg_prep_kernel(int P, int K, const double *__restrict__ theta, 
 //   S[r][a][b][c] += sum_g th_g[a] * M_{r,g}[b][c]
 // One CTA per chunk of genes; thread = cell (a, b, c) for S, thread = (gene, a) for Ntheta.
 // ---------------------------------------------------------------------------------------------
-constexpr int kFinThreads = 256;
+constexpr int kFinThreads = 512;   // 16 warps; two CTAs per SM (grid = 2 x SMs): the kernel is latency-bound, see DESIGN 4.2
 constexpr int kFinWarps = kFinThreads / 32;
 // genes staged in shared memory per pass (both ratings): as many as fit beside p in ~200 KB, at most 48
 template <int K>
 constexpr int fin_chunk()
 {
-    const long avail = 200 * 1024 - 16L * K * K * K;
+    const long avail = 100 * 1024 - 16L * K * K * K;  // two CTAs per SM
     const long per_gene = 16L * K * K + 8L * K;
     const long n = avail / per_gene;
     return n > 48 ? 48 : (n < 1 ? 1 : (int)n);
 }
 
 template <int K>
-__global__ void __launch_bounds__(kFinThreads)
+__global__ void __launch_bounds__(kFinThreads, 2)
     em_finalize_kernel(int P, const double *__restrict__ theta, const double *__restrict__ p,
                        const double *__restrict__ Mg, double *__restrict__ stats)
 {
@@ -1014,7 +1016,7 @@ static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_ro
                                                 (int)fin_smem_bytes<K>()));
             fin_attr = true;
         }
-        int grid = sm_count();
+        int grid = 2 * sm_count();
         if (grid > P) grid = P;
         em_finalize_kernel<K><<<grid, kFinThreads, fin_smem_bytes<K>(), st>>>(P, theta, p, ws, stats);
         TIP_CHECK_CUDA(cudaGetLastError());
