@@ -438,7 +438,12 @@ __global__ void __launch_bounds__(32, MINB)
             const double *ta_p = row;  // walked separately so that `a` only ever indexes the constant bank
             double *tt_p = crow;
             // (A per-lane ld.const prefetch of the next a-slice was tried against the 88 % constant-cache hit rate
-            // ncu reports: the divergent constant access serialises and costs 35 % - not kept.)
+            // ncu reports: the divergent constant access serialises and costs 35 % - not kept.  88 % is exactly one
+            // miss per 64-byte line of 8 doubles: the 8 KB table of a rating is streamed once per tile and nothing
+            // survives until the next walk.  What those misses cost was measured by aliasing every a-slab onto the
+            // first one (wrong results, timing only): 0.254 -> 0.230 ms at 800 k links, 2.45 -> 2.15 ms at 10 M,
+            // i.e. 10-12 %.  A uniform prefetch needs uniform registers, which are what limits the load lookahead
+            // already; unrolling the a-loop by 2 changed nothing.)
             if constexpr (!SEG)
 #pragma unroll 1
             for (int a = 0; a < K; ++a) {
@@ -546,6 +551,10 @@ __global__ void __launch_bounds__(32, MINB)
                 }
             }
             // slots b, c
+            // (Tried: all 64 bulk reductions of a tile issued by lane 0 in an unrolled loop over the links, instead of
+            // two per lane - ptxas wraps the uniform-datapath UBLKRED of each lane in an elect-one-lane loop, 16 % of
+            // the kernel in the round-1 capture.  The single-lane loop still gets a one-trip elect loop per
+            // instruction and serialises the address set-up: 0.274 vs 0.258 ms at 800 k links - not kept.)
             if (K % 2 == 0 && !red_scatter) {
                 // one bulk add-reduction per (link, slot): the 8K-byte row goes to the TMA unit
                 fence_async_smem();
