@@ -433,3 +433,56 @@ def test_cli_writes_reference_shaped_sample_files(torch_cuda, tmp_path, capsys):
     assert main(argv) == 0                           # second run: both samples exist and are skipped
     assert os.path.getmtime(os.path.join(out, "Sample_0_K2.csv")) == stamp
     assert "Likelihood has converged" in capsys.readouterr().out
+
+
+def test_cfg1_full_run_matches_reference(torch_cuda, tmp_path):
+    """BASELINE.json configs[0] end to end: 1,000 genes x 100,000 triplets, get_input -> fold -> fold 1 -> K=2 ->
+    100 EM iterations with the likelihood after every one, against the record the unmodified reference produced
+    (oracle/gen_golden_cfg1.py, ~2.5 min of CPython there).  Inputs are regenerated here and pinned by sha256."""
+    import hashlib
+    from trigenicinteractionpredictor_b200 import Model, synth
+    with open(os.path.join(GOLDEN, "cfg1", "record.json")) as fh:
+        rec = json.load(fh)
+
+    def sha(path):
+        with open(path, "rb") as f:
+            return hashlib.sha256(f.read()).hexdigest()
+
+    g, lab = synth.planted_triplets(1000, 100_000, seed=1, shape="uniform")
+    raw = str(tmp_path / "input_s2.tsv")
+    synth.write_raw_s2(raw, g, lab, synth.gene_names(1000))
+    assert sha(raw) == rec["sha256"]["raw"]
+    m = Model()
+    m.get_input(raw)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        np.random.seed(2)
+        m.fold()
+    finally:
+        os.chdir(cwd)
+    train, test = str(tmp_path / "train1.dat"), str(tmp_path / "test1.dat")
+    assert sha(train) == rec["sha256"]["train"] and sha(test) == rec["sha256"]["test"]      # fold: bit-exact
+    mm = Model()
+    mm.get_traintest(train, test)
+    assert (mm.P, len(mm.links), len(mm.test_links)) == (rec["P"], rec["train_links"], rec["test_links"])
+    random.seed(1000)
+    mm.initialize_parameters(2)
+    like = [mm.compute_likelihood()]
+    for _ in range(100):
+        mm.make_iteration()
+        like.append(mm.compute_likelihood())
+    np.testing.assert_allclose(like, rec["loglik"], rtol=RTOL)                               # every iteration
+    theta = np.array(mm.theta)
+    assert _relerr(theta[rec["theta_rows"]], rec["theta_final_rows"]) < RTOL
+    assert theta.sum() == pytest.approx(rec["theta_final_sum"], rel=RTOL)
+    assert (theta ** 2).sum() == pytest.approx(rec["theta_final_sq"], rel=RTOL)
+    assert _relerr(np.array(mm.pr).reshape(-1), rec["pr_final"]) < RTOL
+    assert mm.compute_likelihood("test") == pytest.approx(rec["heldout"], rel=RTOL)
+    mm.calculate_test_set_results()
+    met = mm.calculate_metrics()
+    assert met[3] == pytest.approx(rec["metrics"][3], abs=1e-6)                              # AUC
+    np.testing.assert_allclose(met[:3], rec["metrics"][:3], atol=1e-3)
+    head = mm.results[:50]
+    assert _relerr([r[0] for r in head], [r[0] for r in rec["results_head"]]) < RTOL
+    assert [r[2] for r in head] == [r[2] for r in rec["results_head"]]

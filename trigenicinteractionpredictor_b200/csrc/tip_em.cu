@@ -204,8 +204,16 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
+// MINB resident warp-CTAs per SM: the register budget is stated with __maxnreg__ (65536 / (32 MINB), multiple of 8)
+// because __launch_bounds__(32, MINB) makes ptxas fall back to 128 registers for every MINB above 12.
+constexpr int em_max_regs(int minb)
+{
+    const int r = 65536 / (32 * minb) / 8 * 8;
+    return r > 255 ? 255 : r;
+}
+
 template <int K, int NBUF, int MINB, bool LL, typename T, bool SEG, bool STREAM = false>
-__global__ void __launch_bounds__(32, MINB)
+__global__ void __launch_bounds__(32) __maxnreg__(em_max_regs(MINB))
     em_fused_kernel(int P, const int4 *__restrict__ rows, int n_tiles, int n_tiles_r0, const double *__restrict__ theta,
                     int p_off0, int p_off1, double *__restrict__ stats, double *__restrict__ Mg,
                     const double *__restrict__ Zg, int red_scatter, StreamArrive sa)
@@ -853,16 +861,16 @@ static int launch_finalize_generic(int P, int K, const double *theta, const doub
 
 static int g_slot_counter = 0;
 
-// TIP_EM_VARIANT=1 (environment, read once): 16 instead of 12 resident warp-CTAs per SM (<=128 registers) for tuning
-// runs; measured equal within noise at K=10.  (A double-buffered gather was measured slower: its shared memory
-// halves the resident warps; the NBUF template parameter keeps that variant buildable.)
+// TIP_EM_VARIANT (environment, read once): 0 = the per-K default chosen in launch_em_fused, 1 / 2 / 3 / 4 = 16 / 14 /
+// 13 / 12 resident warp-CTAs per SM, for tuning runs.  (A double-buffered gather was measured slower: its shared
+// memory halves the resident warps; the NBUF template parameter keeps that variant buildable.)
 static int em_variant()
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("TIP_EM_VARIANT");
         v = e ? atoi(e) : 0;
-        if (v < 0 || v > 1) v = 0;
+        if (v < 0 || v > 4) v = 0;
     }
     return v;
 }
@@ -1011,8 +1019,15 @@ static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_ro
     } else if (with_ll) {
         rc = run_rows<K, 1, 12, true, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st);
     } else {
-        switch (em_variant()) {
+        // resident warp-CTAs per SM (register budget 65536 / (32 MINB)): measured at 1e7 links, K = 10 gains 6-7 % and
+        // K = 8 2.6 % from 16 (128 registers, ~90 bytes of spills) over 12 (158 registers); K = 9 loses 1 %, K <= 6
+        // does not care.  TIP_EM_VARIANT = 1 / 2 / 3 / 4 forces 16 / 14 / 13 / 12 for tuning runs.
+        int v = em_variant();
+        if (v == 0) v = (K == 10 || K == 8) ? 1 : 4;
+        switch (v) {
             case 1: rc = run_rows<K, 1, 16, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
+            case 2: rc = run_rows<K, 1, 14, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
+            case 3: rc = run_rows<K, 1, 13, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
             default: rc = run_rows<K, 1, 12, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
         }
     }
@@ -1277,8 +1292,9 @@ template <int K>
 static int launch_streamed_k(int P, const void *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, double *stats,
                              double *ws, StreamArrive sa, cudaStream_t st)
 {
-    return launch_variant<K, 1, 12, false, double, false, true>(P, reinterpret_cast<const int4 *>(rows), n_rows, n_rows_r0, theta,
-                                                                g_phase_off0, g_phase_off1, stats, ws, st, sa);
+    constexpr int MINB = (K == 10 || K == 8) ? 16 : 12;  // as in launch_em_fused
+    return launch_variant<K, 1, MINB, false, double, false, true>(P, reinterpret_cast<const int4 *>(rows), n_rows, n_rows_r0, theta,
+                                                                  g_phase_off0, g_phase_off1, stats, ws, st, sa);
 }
 
 int launch_em_streamed(int P, int K, const void *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, double *stats,
