@@ -870,7 +870,7 @@ static int em_variant()
     if (v < 0) {
         const char *e = getenv("TIP_EM_VARIANT");
         v = e ? atoi(e) : 0;
-        if (v < 0 || v > 4) v = 0;
+        if (v < 0 || v > 5) v = 0;
     }
     return v;
 }
@@ -1013,7 +1013,15 @@ static int launch_em_fused(int P, const int4 *rows, int64_t n_rows, int64_t n_ro
         if constexpr (K > 4)
             rc = launch_variant<K, 1, 16, false, double, true>(P, rows, n_rows, n_rows_r0, theta, 0, 0, stats, ws, st);
     } else if constexpr (K > 10) {
-        rc = run_rows<K, 1, 12, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st);
+        // K >= 14 prefers 10 resident warps with ~198 registers and no spills (1e7 links: K=16 8.16 vs 8.96 ms,
+        // K=14 6.10 vs 6.27 ms); K = 11..13 stay at 12.  TIP_EM_VARIANT = 2 / 4 / 5 forces 14 / 12 / 10.
+        int v = em_variant();
+        if (v == 0) v = (K >= 14) ? 5 : 4;
+        switch (v) {
+            case 2: rc = run_rows<K, 1, 14, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
+            case 5: rc = run_rows<K, 1, 10, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
+            default: rc = run_rows<K, 1, 12, false, double>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st); break;
+        }
     } else if (f32) {
         rc = run_rows<K, 1, 16, false, float>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st);
     } else if (with_ll) {
