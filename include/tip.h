@@ -144,8 +144,13 @@ int tip_reduce_samples(int S, int64_t T, const double *d_scores, const int32_t *
 
 /* ---- host-buffer entry: n_iter full make_iteration()s with HOST inputs and outputs ----
  * Copies rows/deg/theta/p to the device, runs n_iter x (E-step, M-step), copies theta/p back and
- * synchronises.  Allocates and frees its own device memory (the only function that does).
- * This is the call bench.py times for the end-to-end number. */
+ * synchronises.  Keeps grow-only device scratch for the life of the process (the only function that allocates).
+ * This is the call bench.py times for the end-to-end number.
+ * Plain fp64, K <= 10: the first iteration is STREAMED - one copy of all rows on a side stream, the E-step kernel
+ * polls each tile's rows until they have landed and so follows the DMA front (see tip_em_step_host_rows).  If the
+ * rows do not arrive within 5 s (a platform that cannot run the copy beside the kernel) the call returns -3 and
+ * h_theta / h_p are undefined; the environment variable TIP_HOST_NO_STREAM=1 (read on every call) selects the
+ * copy-in-chunks-then-compute path instead.  One call at a time per process (the scratch is shared). */
 int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t n_rows, int64_t n_rows_r0,
                            const int32_t *h_deg, double *h_theta, double *h_p, int n_iter, unsigned flags);
 

@@ -486,3 +486,41 @@ def test_cfg1_full_run_matches_reference(torch_cuda, tmp_path):
     head = mm.results[:50]
     assert _relerr([r[0] for r in head], [r[0] for r in rec["results_head"]]) < RTOL
     assert [r[2] for r in head] == [r[2] for r in rec["results_head"]]
+
+
+def test_streamed_host_entry_gives_up_cleanly(torch_cuda, monkeypatch):
+    """A streamed E-step whose rows do not arrive in time reports it (-3 / host_rows_arrived() False) instead of
+    hanging, and the copy-then-compute path (TIP_HOST_NO_STREAM=1) of the same entry point still gives the result."""
+    from trigenicinteractionpredictor_b200 import _cabi
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    lib = _cabi.load()
+    P, L, K = 400, 200000, 10
+    g, n0, n1, theta, pr = _random_problem(P, L, K, 91)
+    a = EMEngine(P, K)
+    a.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+    a.set_params(theta, pr)
+    a.em_iteration()
+    th_a, p_a = a.get_params()
+    rows = np.ascontiguousarray(a.train.rows.cpu().numpy())
+    deg = np.ascontiguousarray(a.degrees().astype(np.int32))
+    monkeypatch.setenv("TIP_STREAM_TIMEOUT_US", "0")                    # every wait gives up at once
+    th_h, p_h = np.ascontiguousarray(theta.copy()), np.ascontiguousarray(pr.copy())
+    rcs = [lib.tip_em_iterations_host(P, K, rows.ctypes.data, a.train.n_rows, a.train.n_rows_r0, deg.ctypes.data,
+                                      th_h.ctypes.data, p_h.ctypes.data, 1, 0) for _ in range(3)]
+    # (pageable rows are staged by the driver before the kernel starts, so a call may also succeed: both outcomes are legal)
+    assert all(rc in (0, -3) for rc in rcs)
+    if -3 in rcs:
+        assert b"did not arrive" in lib.tip_last_error()
+    monkeypatch.delenv("TIP_STREAM_TIMEOUT_US")
+    monkeypatch.setenv("TIP_HOST_NO_STREAM", "1")
+    th_h, p_h = np.ascontiguousarray(theta.copy()), np.ascontiguousarray(pr.copy())
+    rc = lib.tip_em_iterations_host(P, K, rows.ctypes.data, a.train.n_rows, a.train.n_rows_r0, deg.ctypes.data,
+                                    th_h.ctypes.data, p_h.ctypes.data, 1, 0)
+    assert rc == 0, lib.tip_last_error()
+    assert _relerr(th_h, th_a) < 1e-11 and _relerr(p_h, p_a) < 1e-11
+    monkeypatch.delenv("TIP_HOST_NO_STREAM")
+    th_h, p_h = np.ascontiguousarray(theta.copy()), np.ascontiguousarray(pr.copy())
+    rc = lib.tip_em_iterations_host(P, K, rows.ctypes.data, a.train.n_rows, a.train.n_rows_r0, deg.ctypes.data,
+                                    th_h.ctypes.data, p_h.ctypes.data, 1, 0)                # streamed again, healthy
+    assert rc == 0, lib.tip_last_error()
+    assert _relerr(th_h, th_a) < 1e-11 and _relerr(p_h, p_a) < 1e-11

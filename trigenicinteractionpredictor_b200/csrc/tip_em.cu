@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(32) __maxnreg__(em_max_regs(MINB))
                 if (__all_sync(0xffffffffu, ok)) break;
                 if (spins == 0) t_start = global_timer_ns();
                 __nanosleep(100);
-                if ((++spins & 255u) == 0 && global_timer_ns() - t_start > sa.timeout_ns) {
+                if (((++spins & 255u) == 0 || sa.timeout_ns == 0) && global_timer_ns() - t_start >= sa.timeout_ns) {
                     stream_dead = true;
                     *sa.err = 1u;
                 }
@@ -1312,7 +1312,10 @@ int launch_em_streamed(int P, int K, const void *rows, int64_t n_rows, int64_t n
     sa.dbg = getenv("TIP_HOST_STREAM_DEBUG") ? reinterpret_cast<unsigned long long *>(err) + 8 : nullptr;
     sa.err = err;
     sa.compact = compact ? 1 : 0;
-    sa.timeout_ns = 5000000000ull;  // 5 s: a host that stopped feeding the copy stream must not hang the GPU
+    // 5 s: a host that stopped feeding the copy stream must not hang the GPU (TIP_STREAM_TIMEOUT_US overrides it, so
+    // that the give-up path can be exercised in tests)
+    const char *to = getenv("TIP_STREAM_TIMEOUT_US");
+    sa.timeout_ns = to ? 1000ull * strtoull(to, nullptr, 10) : 5000000000ull;
     switch (K) {
         case 1: return launch_streamed_k<1>(P, rows, n_rows, n_rows_r0, theta, stats, ws, sa, st);
         case 2: return launch_streamed_k<2>(P, rows, n_rows, n_rows_r0, theta, stats, ws, sa, st);
