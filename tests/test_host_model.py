@@ -157,14 +157,45 @@ def test_product_never_touches_the_oracle_or_the_reference():
     assert "/root/reference" not in bench
 
 
-def test_numeric_methods_refuse_to_run_without_cuda():
-    import torch
-    if torch.cuda.is_available():
-        pytest.skip("CUDA present")
-    from trigenicinteractionpredictor_b200 import _cabi
-    m = _load(BASE, "train1.dat", "test1.dat")
-    random.seed(1)
-    m.initialize_parameters(2)
-    for call in (m.make_iteration, m.compute_likelihood, m.calculate_test_set_results):
-        with pytest.raises(_cabi.TipLibraryError):
-            call()
+@pytest.mark.parametrize("seed", range(8))
+def test_random_files_digest_and_fold_like_the_oracle(tmp_path, monkeypatch, seed):
+    """Random train/test files with everything the digestion has to get right - unsorted names, duplicated lines,
+    conflicting labels, names whose order differs from the order of their ids, ids with different digit counts
+    (the decimal-STRING sort of TIP.py:353), genes seen only in the test file, several tabs before a test label -
+    give the same dictionaries, in the same order, as the oracle (which is pinned to the reference), and the same
+    fold files from the same numpy seed."""
+    from oracle import mmsbm_oracle as orc
+    rng = np.random.default_rng(1000 + seed)
+    P = int(rng.integers(12, 140))
+    names = ["G%d" % v for v in rng.permutation(5000)[:P]]                  # digit counts 1..4, id order != name order
+    def triple():
+        a, b, c = rng.choice(P, size=3, replace=False).tolist()
+        t = [names[a], names[b], names[c]]
+        rng.shuffle(t)
+        return "_".join(t)
+    train = [triple() + "\t" + str(int(rng.random() < 0.3)) + "\n" for _ in range(int(rng.integers(30, 400)))]
+    train += [train[i] for i in rng.integers(0, len(train), size=len(train) // 5)]                      # duplicates
+    train += [train[i].rsplit("\t", 1)[0] + "\t" + ("0" if train[i].strip().endswith("1") else "1") + "\n"
+              for i in rng.integers(0, len(train), size=len(train) // 7)]                               # conflicts
+    extra = ["X%d" % i for i in range(3)]                                                               # test-only genes
+    test = [triple() + ("\t" * int(rng.integers(1, 4))) + str(int(rng.random() < 0.3)) + "\n"
+            for _ in range(int(rng.integers(5, 80)))]
+    test.append("_".join([extra[0], extra[1], names[0]]) + "\t1\n")
+    test.append("_".join([extra[2], names[1], names[2]]) + "\t0\n")
+    tr, te = tmp_path / "train.dat", tmp_path / "test.dat"
+    tr.write_text("".join(train))
+    te.write_text("".join(test))
+    m = Model()
+    m.get_traintest(str(tr), str(te))
+    dg = orc.digest_traintest(train, test)
+    assert m.P == dg.P and m.gene_id == dg.gene_id and m.id_gene == dg.id_gene and m.uniqueg == dg.uniqueg
+    for mine, ref in ((m.links, dg.links), (m.nlinks, dg.nlinks), (m.test_links, dg.test_links)):
+        assert list(mine.items()) == list(ref.items())                      # same keys, same order, same counts
+    np.random.seed(77 + seed)
+    test_txt, train_txt = orc.fold_texts(dg.links, dg.id_gene)
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(77 + seed)
+    m.fold()
+    for i in range(5):
+        assert (tmp_path / ("test%d.dat" % i)).read_text() == test_txt[i]
+        assert (tmp_path / ("train%d.dat" % i)).read_text() == train_txt[i]

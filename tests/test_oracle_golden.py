@@ -184,3 +184,71 @@ def test_training_loop_semantics():
                                                           man["bcheck"])
     assert conv and done - 1 == man["converged_at_iteration"]
     np.testing.assert_allclose(trace, man["checks"], rtol=1e-11)
+
+
+REF_SRC = "/root/reference/src"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_SRC, "TrigenicInteractionPredictor.py")),
+                    reason="the reference only exists in the build container")
+@pytest.mark.parametrize("seed", range(4))
+def test_oracle_against_the_live_reference_on_random_files(tmp_path, monkeypatch, seed):
+    """Build container only: the unmodified reference, imported from /root/reference, digests random files (unsorted
+    names, duplicates, conflicts, test-only genes, ids of different digit counts), folds them and runs two EM
+    iterations; the oracle must agree - dictionaries and fold files exactly, theta / p / log-likelihood to 1e-12."""
+    import contextlib
+    import io
+    import random
+    import sys
+    sys.path.insert(0, REF_SRC)
+    try:
+        import TrigenicInteractionPredictor as ref
+    finally:
+        sys.path.remove(REF_SRC)
+    rng = np.random.default_rng(500 + seed)
+    P = int(rng.integers(10, 60))
+    names = ["G%d" % v for v in rng.permutation(3000)[:P]]
+
+    def triple():
+        t = [names[i] for i in rng.choice(P, size=3, replace=False)]
+        rng.shuffle(t)
+        return "_".join(t)
+    train = [triple() + "\t" + str(int(rng.random() < 0.3)) + "\n" for _ in range(int(rng.integers(60, 250)))]
+    train += [names[i] + "_" + names[(i + 1) % P] + "_" + names[(i + 2) % P] + "\t0\n" for i in range(P)]   # coverage
+    train += [train[i] for i in rng.integers(0, len(train), size=len(train) // 6)]
+    train += [train[i].rsplit("\t", 1)[0] + "\t" + ("0" if train[i].strip().endswith("1") else "1") + "\n"
+              for i in rng.integers(0, len(train), size=len(train) // 8)]
+    test = [triple() + "\t" + str(int(rng.random() < 0.3)) + "\n" for _ in range(30)]
+    tr, te = tmp_path / "train.dat", tmp_path / "test.dat"
+    tr.write_text("".join(train))
+    te.write_text("".join(test))
+    m = ref.Model()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.get_traintest(str(tr), str(te))
+    dg = orc.digest_traintest(train, test)
+    assert (m.P, m.gene_id, m.id_gene, m.uniqueg) == (dg.P, dg.gene_id, dg.id_gene, dg.uniqueg)
+    for mine, ours in ((m.links, dg.links), (m.nlinks, dg.nlinks), (m.test_links, dg.test_links)):
+        assert list(mine.items()) == list(ours.items())
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(9 + seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.fold()
+    np.random.seed(9 + seed)
+    test_txt, train_txt = orc.fold_texts(dg.links, dg.id_gene)
+    for i in range(5):
+        assert (tmp_path / ("test%d.dat" % i)).read_text() == test_txt[i]
+        assert (tmp_path / ("train%d.dat" % i)).read_text() == train_txt[i]
+    K = 3
+    random.seed(40 + seed)
+    m.initialize_parameters(K)
+    random.seed(40 + seed)
+    theta, pr = orc.init_params(dg.P, K)
+    ids, cnt = orc.links_to_arrays(dg.links)
+    tids, tcnt = orc.links_to_arrays(dg.test_links)
+    for _ in range(2):
+        m.make_iteration()
+        theta, pr = orc.em_step_np(theta, pr, ids, cnt)
+    np.testing.assert_allclose(np.array(m.theta), theta, rtol=1e-12)
+    np.testing.assert_allclose(np.array(m.pr), pr, rtol=1e-12)
+    assert m.compute_likelihood() == pytest.approx(orc.loglik_np(theta, pr, ids, cnt), rel=1e-12)
+    assert m.compute_likelihood("test") == pytest.approx(orc.loglik_np(theta, pr, tids, tcnt), rel=1e-12)
