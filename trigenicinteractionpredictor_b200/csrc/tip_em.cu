@@ -216,8 +216,10 @@ template <int K, int NBUF, int MINB, bool LL, typename T, bool SEG, bool STREAM 
 __global__ void __launch_bounds__(32) __maxnreg__(em_max_regs(MINB))
     em_fused_kernel(int P, const int4 *__restrict__ rows, int n_tiles, int n_tiles_r0, const double *__restrict__ theta,
                     int p_off0, int p_off1, double *__restrict__ stats, double *__restrict__ Mg,
-                    const double *__restrict__ Zg, int red_scatter, StreamArrive sa)
+                    const double *__restrict__ Zg, int tune, StreamArrive sa)
 {
+    const int red_scatter = tune & 1;  // bit 0: per-lane REDs instead of bulk reductions (TIP_EM_SCATTER=red);
+                                       // bit 1: stage Z_g of single-gene tiles in shared memory (off: TIP_SEG_ZSMEM=0)
     using C = EmCfg<K, NBUF>;
     constexpr int KP = C::KP, RS = C::RS, K3 = C::K3, CB = C::CB, RC = C::RC, CA = C::CA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -413,34 +415,58 @@ __global__ void __launch_bounds__(32) __maxnreg__(em_max_regs(MINB))
             }
             T dsum = (T)0;
             if constexpr (SEG) {
-                // per-lane pointer to Z of this link's slot-a gene and rating
+                // Z of this link's slot-a gene and rating.  Most tiles lie inside one run of equal slot-a gene (runs are
+                // ~4 tiles long at cfg2): then Z_g is staged once, coalesced, into the th_a slots of the stage - which
+                // this formulation never reads - as zs[b * RS + c], and every lane takes it from there as a shared-memory
+                // broadcast instead of 50 dependent-latency L2 loads per link (long-scoreboard stalls were 41 % of this
+                // kernel, profiles/r1_em_fused_k10_gene_segmented_summary.txt).  Mixed tiles read Z through L1 as before.
                 const double *Zrow = Zg + ((int64_t)r_v * P + me.x) * (K * K);
-#pragma unroll 2
-                for (int b = 0; b < K; ++b) {
-                    const T tbb = (T)row[KP + b];
-                    T y0 = (T)0, y1 = (T)0;
+                const int g0 = __shfl_sync(0xffffffffu, me.x, 0);
+                const bool one_gene = (tune & 2) && __all_sync(0xffffffffu, me.x == g0 && cnt != 0.0);
+                if (one_gene) {
 #pragma unroll
-                    for (int c = 0; c < K; c += 2) {
-                        if constexpr (K % 2 == 0) {
-                            const double2 z = __ldg(reinterpret_cast<const double2 *>(Zrow + b * K + c));
+                    for (int e = lane; e < K * K; e += 32) {
+                        const int zb = e / K, zc = e - zb * K;
+                        stage[zb * RS + zc] = __ldg(Zrow + e);
+                    }
+                    __syncwarp();
+                }
+                auto seg_phase_a = [&](auto zpair) {
+#pragma unroll 2
+                    for (int b = 0; b < K; ++b) {
+                        const T tbb = (T)row[KP + b];
+                        T y0 = (T)0, y1 = (T)0;
+#pragma unroll
+                        for (int c = 0; c < K; c += 2) {
+                            const double2 z = zpair(b, c);   // z.y is not used for the last column of an odd K
                             y0 = fma((T)z.x, tc[c], y0);
                             w[c] = fma(tbb, (T)z.x, w[c]);
-                            y1 = fma((T)z.y, tc[c + 1], y1);
-                            w[c + 1] = fma(tbb, (T)z.y, w[c + 1]);
-                        } else {
-                            const T z0 = (T)__ldg(Zrow + b * K + c);
-                            y0 = fma(z0, tc[c], y0);
-                            w[c] = fma(tbb, z0, w[c]);
                             if (c + 1 < K) {
-                                const T z1 = (T)__ldg(Zrow + b * K + c + 1);
-                                y1 = fma(z1, tc[c + 1], y1);
-                                w[c + 1] = fma(tbb, z1, w[c + 1]);
+                                y1 = fma((T)z.y, tc[c + 1], y1);
+                                w[c + 1] = fma(tbb, (T)z.y, w[c + 1]);
                             }
                         }
+                        const T tby = tbb * (y0 + y1);
+                        dsum += tby;
+                        crow[CA + b] = (double)tby;  // unscaled slot-b contribution, multiplied by s below
                     }
-                    const T tby = tbb * (y0 + y1);
-                    dsum += tby;
-                    crow[CA + b] = (double)tby;  // unscaled slot-b contribution, multiplied by s below
+                };
+                if (one_gene) {
+                    seg_phase_a([&](int b, int c) {
+                        if constexpr (K % 2 == 0) {
+                            return *reinterpret_cast<const double2 *>(stage + b * RS + c);
+                        } else {
+                            return make_double2(stage[b * RS + c], (c + 1 < K) ? stage[b * RS + c + 1] : 0.0);
+                        }
+                    });
+                } else {
+                    seg_phase_a([&](int b, int c) {
+                        if constexpr (K % 2 == 0) {
+                            return __ldg(reinterpret_cast<const double2 *>(Zrow + b * K + c));
+                        } else {
+                            return make_double2(__ldg(Zrow + b * K + c), (c + 1 < K) ? __ldg(Zrow + b * K + c + 1) : 0.0);
+                        }
+                    });
                 }
             }
             const double *ta_p = row;  // walked separately so that `a` only ever indexes the constant bank
@@ -877,6 +903,16 @@ static int em_variant()
 
 // TIP_EM_SCATTER=red (environment, read once): slot-b/c contributions with per-lane red.global.add.f64 instead of
 // the bulk add-reductions, for A/B timing (measured equal within noise at K=10; both give the same statistics)
+static int em_seg_zsmem()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TIP_SEG_ZSMEM");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+
 static int em_red_scatter()
 {
     static int v = -1;
@@ -911,7 +947,7 @@ static int launch_variant(int P, const int4 *rows, int64_t n_rows, int64_t n_row
     if (grid < 1) grid = 1;
     em_fused_kernel<K, NBUF, MINB, LL, T, SEG, STREAM><<<grid, 32, C::SMEM, st>>>(
         P, rows, (int)n_tiles, (int)(n_rows_r0 / 32), theta, p_off0, p_off1, stats, Mg,
-        SEG ? Mg + 2 * (size_t)P * K * K : nullptr, em_red_scatter(), sa);
+        SEG ? Mg + 2 * (size_t)P * K * K : nullptr, em_red_scatter() | (em_seg_zsmem() << 1), sa);
     TIP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
