@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(32) __maxnreg__(em_max_regs(MINB))
                 // ~4 tiles long at cfg2): then Z_g is staged once, coalesced, into the th_a slots of the stage - which
                 // this formulation never reads - as zs[b * RS + c], and every lane takes it from there as a shared-memory
                 // broadcast instead of 50 dependent-latency L2 loads per link (long-scoreboard stalls were 41 % of this
-                // kernel, profiles/r1_em_fused_k10_gene_segmented_summary.txt).  Mixed tiles read Z through L1 as before.
+                // kernel, profiles/r1_em_fused_k10_gene_segmented_before_zstage_summary.txt).  Mixed tiles read Z through L1 as before.
                 const double *Zrow = Zg + ((int64_t)r_v * P + me.x) * (K * K);
                 const int g0 = __shfl_sync(0xffffffffu, me.x, 0);
                 const bool one_gene = (tune & 2) && __all_sync(0xffffffffu, me.x == g0 && cnt != 0.0);
