@@ -433,6 +433,12 @@ def test_cli_writes_reference_shaped_sample_files(torch_cuda, tmp_path, capsys):
     assert main(argv) == 0                           # second run: both samples exist and are skipped
     assert os.path.getmtime(os.path.join(out, "Sample_0_K2.csv")) == stamp
     assert "Likelihood has converged" in capsys.readouterr().out
+    # --mode segmented: the gene-segmented E-step through the same command line, same report to 1e-9
+    out2 = str(tmp_path / "seg") + os.sep
+    os.makedirs(out2)
+    assert main(argv[:-4] + ["-n", "1", "-o", out2, "--seed", "1000", "--mode", "segmented"]) == 0
+    got2 = open(os.path.join(out2, "Sample_0_K2.csv"), encoding="utf-8").read().split("\n")
+    assert float(got2[0].split("\t")[1]) == pytest.approx(float(exp[0].split("\t")[1]), rel=1e-9)
 
 
 def test_cfg1_full_run_matches_reference(torch_cuda, tmp_path):

@@ -115,6 +115,7 @@ def test_cli_rejects_bad_arguments(tmp_path, capsys):
     assert main(["-t", "/nonexistent", "-e", os.path.join(BASE, "test1.dat")]) == 2
     assert main(["-o", str(tmp_path / "missing"), "-t", os.path.join(BASE, "train1.dat")]) == 2
     assert main(["-h"]) == 0
+    assert main(["--mode", "tf32", "-t", os.path.join(BASE, "train1.dat"), "-e", os.path.join(BASE, "test1.dat")]) == 2
 
 
 def test_shard_bounds_and_sample_assignment():

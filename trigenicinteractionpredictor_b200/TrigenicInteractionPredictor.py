@@ -482,7 +482,9 @@ class Model:
 
 # ----------------------------------------------------------------------------------------------
 # command line: same flags, defaults, file naming, skip-if-exists and convergence rule as
-# TIP.py:1148-1279.  Additions: --seed (instead of os.getpid()), --device, --dist samples|links.
+# TIP.py:1148-1279.  Additions: --seed (instead of os.getpid()), --device, --dist samples|links,
+# --mode fp64|segmented|fp32 (E-step formulation: K^3 per link, gene-segmented 2K^2 per link - same results to
+# rounding and the fastest -, or fp32-compute / fp64-accumulate within 1e-5).
 # ----------------------------------------------------------------------------------------------
 def train_sample(model, k, iterations, fcheck, bcheck, outfile=None, verbose=True, log=print):
     """One random restart (TIP.py:1260-1279).  Returns (converged, iterations_done, checks)."""
@@ -523,11 +525,11 @@ def main(argv=None):
     iterations, num_samples, sample_ini, fcheck, bcheck = 10000, 100, 0, 25, 100
     train = test = None
     outpath, argk = "", 1
-    seed, device, dist_mode = None, None, "none"
+    seed, device, dist_mode, mode_flags = None, None, "none", 0
     try:
         opts, _ = getopt.getopt(argv, "hi:n:s:f:b:o:t:e:k:",
                                 ["help", "num_iterations=", "num_samples=", "sample_ini=", "fcheck=", "bcheck=",
-                                 "out=", "train=", "test=", "k=", "seed=", "device=", "dist="])
+                                 "out=", "train=", "test=", "k=", "seed=", "device=", "dist=", "mode="])
         for opt, arg in opts:
             if opt in ("-h", "--help"):
                 print(__doc__)
@@ -585,6 +587,10 @@ def main(argv=None):
                 if arg not in ("none", "samples", "links"):
                     raise ValueError
                 dist_mode = arg
+            elif opt == "--mode":
+                if arg not in ("fp64", "segmented", "fp32"):
+                    raise ValueError
+                mode_flags = {"fp64": 0, "segmented": 8, "fp32": 2}[arg]       # TIP_EM_* of include/tip.h
     except getopt.GetoptError:
         print("Argument error. Aborting")
         return 2
@@ -608,7 +614,7 @@ def main(argv=None):
           "\n Output directory is " + str(outpath) + "\nK value (number of groups) is " + str(argk) +
           ".\nLikelihood will be computed every " + str(fcheck) + " num_iterations after iteration number " + str(bcheck))
 
-    model = Model(device=device, group=None if dist_mode != "links" else _dist.td.group.WORLD)
+    model = Model(device=device, group=None if dist_mode != "links" else _dist.td.group.WORLD, flags=mode_flags)
     model.get_traintest(train, test)
     print("\nStarting algorithm...")
     samples = range(sample_ini, sample_ini + int(num_samples))
