@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Small end-to-end pass for compute-sanitizer (memcheck / racecheck / initcheck): every kernel family once on a tiny
-problem - K=10 fused + finalize, K=4 private-S, K=7 odd-K scatter, gene-segmented, K=20 large, streamed host rows
+"""Small end-to-end pass over every kernel family once on a tiny problem (written for compute-sanitizer memcheck /
+racecheck; the sanitizer is closed on this GPU pool, so it serves as a quick all-kernels smoke pass) - K=10 fused + finalize, K=4 private-S, K=7 odd-K scatter, gene-segmented, K=20 large, streamed host rows
 (both formats), likelihood (fused + segmented), scoring, metrics, reducer.
     compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
 import os
