@@ -525,10 +525,12 @@ def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
                "front (link-sharded, %s exchange)" % args.exchange)
     if not streamed:
         api += " - NOT streamed on this box (the streamed step gave up waiting for its rows): copy, then compute"
-    return {"value": L_total * steps / dt, "unit": UNIT, "streamed": streamed, "h2d_bytes_per_step": int(n_rows * 8 + fixed),
-            "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt / steps, "api": api,
+    # bytes are whole-job like `value`: every rank copies its own shard's rows plus the replicated parameters
+    return {"value": L_total * steps / dt, "unit": UNIT, "streamed": streamed,
+            "h2d_bytes_per_step": int(n_rows * 8 + fixed) * world, "d2h_bytes_per_step": int(d2h) * world,
+            "bytes_are": "summed over the %d rank(s)" % world, "ms_per_step": 1e3 * dt / steps, "api": api,
             "rows16": {"value": L_total * steps / dt16, "ms_per_step": 1e3 * dt16 / steps,
-                       "h2d_bytes_per_step": int(n_rows * 16 + fixed)}}
+                       "h2d_bytes_per_step": int(n_rows * 16 + fixed) * world}}
 
 
 def main():
