@@ -130,6 +130,26 @@ def test_em_trace_dups_numpy():
     _trace_check(DUPS, 3, "train.dat", "test.dat", 1001, 3, orc.em_step_np, 1e-12)
 
 
+KUZMIN = os.path.join(GOLDEN, "kuzmin")
+
+
+@pytest.mark.parametrize("K,iters", [(3, 5), (10, 3)])
+def test_em_trace_kuzmin_hub_shaped(K, iters):
+    """Hub-shaped data (query pair x array gene, oracle/gen_golden_kuzmin.py): digestion bit-exact incl. where the
+    hubs land under the decimal-string slot order, EM trace / scores / metrics of the unmodified reference."""
+    info = json.load(open(os.path.join(KUZMIN, "info.json")))
+    _check_digest(_digest(KUZMIN), json.load(open(os.path.join(KUZMIN, "digest.json"))))
+    dg, tr, th, pr, tids = _trace_check(KUZMIN, K, "train1.dat", "test1.dat", 1000, iters, orc.em_step_np, 1e-12)
+    ids, _ = orc.links_to_arrays(dg.links)
+    deg = [np.bincount(ids[:, s], minlength=dg.P) for s in range(3)]
+    assert [int(d.max()) for d in deg] == info["max_degree_per_slot"]
+    assert min(info["max_degree_per_slot"]) > 100           # hubs in every slot
+    np.testing.assert_allclose(orc.scores_np(th, pr, tids), tr["scores_test_order"], rtol=1e-12)
+    res = orc.test_results(tr["scores_test_order"], dg.test_links)
+    assert [r[1] for r in res] == tr["result_keys"].tolist()
+    assert orc.metrics(res, dg.links, len(dg.test_links)) == tr["metrics"].tolist()
+
+
 @pytest.mark.parametrize("K", [2, 3])
 def test_em_trace_c_bit_exact(K):
     """The literal-order C restatement reproduces CPython's doubles bit for bit."""

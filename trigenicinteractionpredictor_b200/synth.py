@@ -22,6 +22,7 @@ __all__ = [
     "write_dat",
     "write_raw_s2",
     "planted_links_soa",
+    "kuzmin_links_soa",
 ]
 
 
@@ -116,6 +117,50 @@ def write_raw_s2(path: str, g: np.ndarray, lab: np.ndarray, names: list[str]) ->
             score, pval = ("-0.5", "0.01") if r else ("0.0", "0.5")
             fh.write("\t".join(["Q%d" % n, names[a] + "+" + names[b], "A%d" % n, names[c], "trigenic",
                                 score, pval, "novel" if r else "none"]) + "\n")
+
+
+def _decimal_string_rank(ids, xp):
+    """Sort key that orders non-negative ids like Python orders their decimal strings (TIP.py:353 sorts the ids
+    of a triplet AS STRINGS, so "10" < "9"): digits left-aligned to 10 places, shorter string first on a tie
+    ("1" < "10").  Works on numpy arrays and torch tensors (int64)."""
+    nd = xp.ones_like(ids)
+    for d in range(1, 10):
+        nd = nd + (ids >= 10 ** d)
+    return (ids * 10 ** (10 - nd)) * 16 + nd
+
+
+def kuzmin_links_soa(P: int, n_links: int, *, seed: int = 1, device=None, n_query: int | None = None):
+    """Hub-shaped links at bench scale: (query pair) x (array gene) like the Kuzmin-2018 screen the reference
+    digests (TIP.py:272-273), `n_query` (default round(sqrt(P)), 77 at P = 6000) query genes of degree
+    ~2 n_links / n_query, every other gene an array gene.
+
+    Ids are what the reference's digestion would give them: by first appearance (TIP.py:337-341), so the query
+    genes - present in almost every line - hold the smallest ids and the array genes follow in random order; and
+    the three ids of a link are put in the key's slot order, the DECIMAL-STRING order of TIP.py:353, so a hub
+    lands in slot a, b or c exactly where it would in the reference ("1234" < "42" < "5").
+    Returns int32 (g1, g2, g3, label) in slot order, torch tensors on `device` (numpy when device is None)."""
+    nq = n_query or max(4, int(round(P ** 0.5)))
+    if device is None:
+        rng = np.random.default_rng(seed)
+        q1 = rng.integers(0, nq, n_links)
+        q2 = (q1 + 1 + rng.integers(0, nq - 1, n_links)) % nq
+        arr = rng.integers(nq, P, n_links)
+        ids = np.stack([q1, q2, arr], axis=1).astype(np.int64)
+        order = np.argsort(_decimal_string_rank(ids, np), axis=1, kind="stable")
+        ids = np.take_along_axis(ids, order, axis=1).astype(np.int32)
+        lab = (rng.random(n_links) < 0.1).astype(np.int32)
+        return ids[:, 0].copy(), ids[:, 1].copy(), ids[:, 2].copy(), lab
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    q1 = torch.randint(0, nq, (n_links,), device=device, generator=gen)
+    q2 = (q1 + 1 + torch.randint(0, nq - 1, (n_links,), device=device, generator=gen)) % nq
+    arr = torch.randint(nq, P, (n_links,), device=device, generator=gen)
+    ids = torch.stack([q1, q2, arr], dim=1)
+    order = torch.argsort(_decimal_string_rank(ids, torch), dim=1, stable=True)
+    ids = torch.gather(ids, 1, order).to(torch.int32)
+    lab = (torch.rand(n_links, device=device, generator=gen) < 0.1).to(torch.int32)
+    return ids[:, 0].contiguous(), ids[:, 1].contiguous(), ids[:, 2].contiguous(), lab
 
 
 def planted_links_soa(P: int, n_links: int, *, seed: int = 1, device=None, k_star: int = 4):
