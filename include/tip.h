@@ -53,6 +53,10 @@ extern "C" {
                                    2K^2 instead of 2K^3 FMA (same results to rounding); the kernel is then bound by
                                    the theta gather and the reductions, not by the FMA pipe.  K = 17..32 always
                                    runs this formulation (its only specialised kernel) */
+#define TIP_EM_SLOT_SEGMENTED 32u /* any K, fp64: all three theta statistics and the p statistic accumulated per run of
+                                   equal gene, in three sort orders of the links (4K^2 FMA per link, no per-link atomics:
+                                   hub genes cost nothing extra).  d_rows then holds the three orders back to back, n_rows
+                                   rows each: the packed rows, then tip_order_rows' output */
 #define TIP_EM_WITH_LOGLIK 4u   /* also accumulate the log-likelihood by-product (last stats slot); off by
                                    default because the log costs ~2 % of a K=10 step and the training loop only
                                    needs the likelihood every `fcheck` iterations (tip_loglik) */
@@ -78,6 +82,17 @@ int tip_pack_rows_workspace_bytes(int64_t L, size_t *bytes);
 int tip_pack_rows(const int32_t *d_g1, const int32_t *d_g2, const int32_t *d_g3, const int32_t *d_n0,
                   const int32_t *d_n1, int64_t L, int P, void *d_ws, size_t ws_bytes, void *d_rows,
                   int64_t *h_n_rows, int64_t *h_part, int32_t *d_deg, void *stream);
+
+/* ---- the slot-b and slot-c orders of the packed rows (TIP_EM_SLOT_SEGMENTED) ----
+ * in : d_rows [n_rows] packed rows of tip_pack_rows (ordered by rating, then slot-a gene)
+ * out: d_rows_bc [2 * n_rows]: the same links ordered by (rating, slot-b gene), then by (rating, slot-c gene); a row is
+ *      {gene of the ordering slot, slot-a gene (or slot-a for c), the remaining gene, position of the link in d_rows},
+ *      i.e. {b, a, c, pos} and {c, a, b, pos}; padding rows are {0, 0, 0, -1}.  The rating blocks keep their sizes, so
+ *      n_rows and n_rows_r0 describe all three orders.  Stable: links of one gene stay in slot-a order.
+ * Asynchronous on `stream`; digestion time, not iteration time. */
+int tip_order_rows_workspace_bytes(int64_t n_rows, size_t *bytes);
+int tip_order_rows(const void *d_rows, int64_t n_rows, int64_t n_rows_r0, void *d_ws, size_t ws_bytes, void *d_rows_bc,
+                   void *stream);
 
 /* ---- Model.make_iteration, E-step half (TIP.py:987-1012) ----
  * Zeroes d_stats, then accumulates the statistics of `n_rows` packed rows under (d_theta, d_p).

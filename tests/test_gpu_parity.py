@@ -147,6 +147,124 @@ def test_gene_segmented_mode_reference_trace(torch_cuda):
         assert m.compute_likelihood() == pytest.approx(tr["loglik"][it + 1], rel=RTOL)
 
 
+KUZMIN = os.path.join(GOLDEN, "kuzmin")
+
+
+@pytest.mark.parametrize("flags", [None, 32, 0, 8, 1], ids=["default", "slots", "k3", "gene_seg", "anyK"])
+@pytest.mark.parametrize("K,iters", [(3, 5), (10, 3)])
+def test_em_trace_matches_reference_on_hub_shaped_links(torch_cuda, K, iters, flags):
+    """Kuzmin shape: 20 query genes carry every link (hubs in all three key slots).  theta, p, log-likelihood per
+    iteration within 1e-9 of the unmodified reference, scores 1e-9, AUC 1e-6 - for every E-step formulation."""
+    tr = np.load(os.path.join(KUZMIN, "trace_K%d.npz" % K))
+    m = _model(KUZMIN, "train1.dat", "test1.dat", flags=flags)
+    random.seed(1000)
+    m.initialize_parameters(K)
+    assert np.array_equal(np.array(m.theta), tr["theta0"])
+    assert m.compute_likelihood() == pytest.approx(tr["loglik"][0], rel=RTOL)
+    for it in range(iters):
+        m.make_iteration()
+        assert _relerr(m.theta, tr["theta%d" % (it + 1)]) < RTOL, "theta iteration %d" % (it + 1)
+        assert _relerr(m.pr, tr["pr%d" % (it + 1)]) < RTOL, "p iteration %d" % (it + 1)
+        assert m.compute_likelihood() == pytest.approx(tr["loglik"][it + 1], rel=RTOL)
+    assert m.compute_likelihood("test") == pytest.approx(tr["heldout"][0], rel=RTOL)
+    m.calculate_test_set_results()
+    assert _relerr(m._scores.cpu().numpy(), tr["scores_test_order"]) < RTOL
+    assert m.calculate_metrics()[3] == pytest.approx(tr["metrics"][3], abs=1e-6)
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 10])
+def test_slot_segmented_mode_reference_trace(torch_cuda, K):
+    """TIP_EM_SLOT_SEGMENTED (flag 32) on the reference trace of the base case, every K the golden set has."""
+    tr = np.load(os.path.join(BASE, "trace_K%d.npz" % K))
+    m = _model(BASE, "train1.dat", "test1.dat", flags=32)
+    random.seed(1000)
+    m.initialize_parameters(K)
+    for it in range(5):
+        m.make_iteration()
+        assert _relerr(m.theta, tr["theta%d" % (it + 1)]) < RTOL, "theta iteration %d" % (it + 1)
+        assert _relerr(m.pr, tr["pr%d" % (it + 1)]) < RTOL, "p iteration %d" % (it + 1)
+        assert m.compute_likelihood() == pytest.approx(tr["loglik"][it + 1], rel=RTOL)
+
+
+def test_slot_segmented_duplicates_and_conflicts(torch_cuda):
+    tr = np.load(os.path.join(DUPS, "trace_K3.npz"))
+    m = _model(DUPS, "train.dat", "test.dat", flags=32)
+    random.seed(1001)
+    m.initialize_parameters(3)
+    for it in range(3):
+        m.make_iteration()
+        assert _relerr(m.theta, tr["theta%d" % (it + 1)]) < RTOL
+        assert _relerr(m.pr, tr["pr%d" % (it + 1)]) < RTOL
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 16, 17, 20, 24, 25, 32])
+@pytest.mark.parametrize("shape", ["uniform", "hubs"])
+def test_slot_segmented_mode_matches_oracle(torch_cuda, K, shape):
+    """Statistics of the slot-segmented E-step against the NumPy oracle (1e-11), uniform links and links whose three
+    slots are all dominated by a handful of hub genes; every accumulator-block count (K <= 8, 16, 24, 32)."""
+    from oracle import mmsbm_oracle as orc
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    from trigenicinteractionpredictor_b200 import synth
+    P, L = 300, 6000 if K <= 10 else (2000 if K <= 16 else 700)
+    g, n0, n1, theta, pr = _random_problem(P, L, K, 500 + K)
+    if shape == "hubs":
+        a, b, c, lab = synth.kuzmin_links_soa(P, L, seed=K, n_query=6)
+        g = np.stack([a, b, c], axis=1).astype(np.int32)
+        g[:P, 0] = np.arange(P)
+        n0, n1 = (1 - lab).astype(np.int32), lab.astype(np.int32)
+        n0[5:40:7] += 2                             # repeated sightings: counts above one
+    cnt = np.stack([n0, n1], axis=1).astype(np.int64)
+    ent, enp, deg = orc.em_step_np(theta, pr, g.astype(np.int64), cnt, return_stats=True)
+    th1, pr1 = orc.normalise_np(ent, enp, deg)
+    eng = EMEngine(P, K, flags=32)
+    eng.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+    eng.set_params(theta, pr)
+    eng.em_step()
+    st = eng.stats.cpu().numpy()
+    nth = st[: P * K].reshape(P, K)
+    S = st[P * K: P * K + 2 * K ** 3].reshape(2, K, K, K)
+    assert _relerr(nth, ent) < 1e-11, "Ntheta K=%d" % K
+    assert _relerr(pr * np.moveaxis(S, 0, -1), np.maximum(enp, 1e-300)) < 1e-11, "Np K=%d" % K
+    eng.normalise()
+    th, p = eng.get_params()
+    assert _relerr(th, th1) < 1e-11 and _relerr(p, pr1) < 1e-11
+    eng.set_params(theta, pr)
+    eng.em_iterations(5)                            # CUDA-graph replay of the four-kernel E-step
+    tho, pro = theta, pr
+    for _ in range(5):
+        tho, pro = orc.em_step_np(tho, pro, g.astype(np.int64), cnt)
+    th, p = eng.get_params()
+    assert _relerr(th, tho) < 1e-10 and _relerr(p, pro) < 1e-10
+
+
+def test_order_rows_bit_exact(torch_cuda):
+    """tip_order_rows against NumPy: the slot-b / slot-c orders are stable sorts of the packed rows by (rating, gene),
+    rating blocks keep their padded sizes, every row carries the position of its link in the slot-a order."""
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    rng = np.random.default_rng(9)
+    P, L = 200, 5003
+    g = rng.integers(0, P, size=(L, 3)).astype(np.int32)
+    n0 = rng.integers(0, 2, size=L).astype(np.int32)
+    n1 = (1 - n0) * rng.integers(0, 2, size=L).astype(np.int32)
+    eng = EMEngine(P, 5, flags=32)
+    eng.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+    t = eng.train
+    rows3 = t.rows3.cpu().numpy()
+    n, n_r0 = t.n_rows, t.n_rows_r0
+    ra = rows3[:n]
+    assert np.array_equal(ra, t.rows.cpu().numpy())
+    for slot, blk in ((1, rows3[n: 2 * n]), (2, rows3[2 * n:])):
+        exp = np.zeros_like(ra)
+        exp[:, 3] = -1
+        for lo, hi in ((0, n_r0), (n_r0, n)):
+            idx = np.arange(lo, hi)
+            live = idx[(ra[lo:hi, 3] >> 1) > 0]
+            order = live[np.argsort(ra[live, slot], kind="stable")]
+            other = 2 if slot == 1 else 1
+            exp[lo: lo + len(order)] = np.stack([ra[order, slot], ra[order, 0], ra[order, other], order], axis=1)
+        assert np.array_equal(blk, exp)
+
+
 def test_fp32_mode_is_rejected_where_it_does_not_exist(torch_cuda):
     from trigenicinteractionpredictor_b200._cabi import TipLibraryError
     from trigenicinteractionpredictor_b200.engine import EMEngine

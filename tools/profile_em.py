@@ -14,10 +14,14 @@ K = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 800_000
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 flags = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+shape = sys.argv[5] if len(sys.argv) > 5 else "uniform"
 P = 6000
 dev = torch.device("cuda:0")
 eng = EMEngine(P, K, device=dev, flags=flags)
-g1, g2, g3, lab = synth.planted_links_soa(P, L, seed=100, device=dev)
+if shape == "kuzmin":
+    g1, g2, g3, lab = synth.kuzmin_links_soa(P, L, seed=100, device=dev)
+else:
+    g1, g2, g3, lab = synth.planted_links_soa(P, L, seed=100, device=dev)
 g1[:P] = torch.arange(P, dtype=torch.int32, device=dev)
 eng.set_train_links(g1, g2, g3, 1 - lab, lab)
 rng = np.random.default_rng(0)

@@ -38,7 +38,7 @@ class Model:
     """State and methods of the MMSBM predictor (TIP.py:33).  `device`/`group`/`flags` are additions:
     the CUDA device to use, a torch.distributed group for link-sharded training, and TIP_EM_* flags."""
 
-    def __init__(self, device=None, group=None, flags: int = 0):
+    def __init__(self, device=None, group=None, flags: int | None = None):
         # --- reference attributes (TIP.py:39-88) ---
         self.id_gene = {}
         self.gene_id = {}
@@ -483,8 +483,9 @@ class Model:
 # ----------------------------------------------------------------------------------------------
 # command line: same flags, defaults, file naming, skip-if-exists and convergence rule as
 # TIP.py:1148-1279.  Additions: --seed (instead of os.getpid()), --device, --dist samples|links,
-# --mode fp64|segmented|fp32 (E-step formulation: K^3 per link, gene-segmented 2K^2 per link - same results to
-# rounding and the fastest -, or fp32-compute / fp64-accumulate within 1e-5).
+# --mode auto|slots|fp64|segmented|fp32 (E-step formulation: slot-segmented 4K^2 per link without per-link atomics - the
+# default for K >= 5 -, K^3 per link, gene-segmented 2K^2 per link - all the same results to rounding -, or
+# fp32-compute / fp64-accumulate within 1e-5).
 # ----------------------------------------------------------------------------------------------
 def train_sample(model, k, iterations, fcheck, bcheck, outfile=None, verbose=True, log=print):
     """One random restart (TIP.py:1260-1279).  Returns (converged, iterations_done, checks)."""
@@ -525,7 +526,7 @@ def main(argv=None):
     iterations, num_samples, sample_ini, fcheck, bcheck = 10000, 100, 0, 25, 100
     train = test = None
     outpath, argk = "", 1
-    seed, device, dist_mode, mode_flags = None, None, "none", 0
+    seed, device, dist_mode, mode_flags = None, None, "none", None
     try:
         opts, _ = getopt.getopt(argv, "hi:n:s:f:b:o:t:e:k:",
                                 ["help", "num_iterations=", "num_samples=", "sample_ini=", "fcheck=", "bcheck=",
@@ -588,9 +589,9 @@ def main(argv=None):
                     raise ValueError
                 dist_mode = arg
             elif opt == "--mode":
-                if arg not in ("fp64", "segmented", "fp32"):
+                if arg not in ("auto", "slots", "fp64", "segmented", "fp32"):
                     raise ValueError
-                mode_flags = {"fp64": 0, "segmented": 8, "fp32": 2}[arg]       # TIP_EM_* of include/tip.h
+                mode_flags = {"auto": None, "slots": 32, "fp64": 0, "segmented": 8, "fp32": 2}[arg]   # TIP_EM_* of include/tip.h
     except getopt.GetoptError:
         print("Argument error. Aborting")
         return 2

@@ -22,6 +22,7 @@ TIP_EM_FP32_COMPUTE = 2
 TIP_EM_WITH_LOGLIK = 4
 TIP_EM_GENE_SEGMENTED = 8
 TIP_ROWS_COMPACT8 = 16
+TIP_EM_SLOT_SEGMENTED = 32
 
 # name -> (restype, argtypes); must list every function include/tip.h declares (tests check this)
 SIGNATURES = {
@@ -32,6 +33,8 @@ SIGNATURES = {
     "tip_pack_rows_workspace_bytes": (c_int, [c_int64, _psz]),
     "tip_pack_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t,
                               c_void_p, _pi64, _pi64, c_void_p, c_void_p]),
+    "tip_order_rows_workspace_bytes": (c_int, [c_int64, _psz]),
+    "tip_order_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "tip_em_workspace_bytes": (c_int, [c_int, c_int, c_int64, c_uint, _psz]),
     "tip_em_step": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                             c_uint, c_void_p]),

@@ -28,6 +28,7 @@ static bool uses_tuned(int K, unsigned flags)
     return !(flags & (TIP_EM_WITH_LOGLIK | TIP_EM_FP32_COMPUTE));
 }
 static bool seg_flag(unsigned flags) { return (flags & TIP_EM_GENE_SEGMENTED) != 0; }
+static bool seg3_flag(unsigned flags) { return (flags & TIP_EM_SLOT_SEGMENTED) != 0; }
 
 }  // namespace tip
 
@@ -41,6 +42,10 @@ extern "C" int64_t tip_stats_len(int P, int K) { return (int64_t)P * K + 2ll * K
 extern "C" int tip_em_workspace_bytes(int P, int K, int64_t n_rows, unsigned flags, size_t *bytes)
 {
     TIP_REQUIRE(bytes != nullptr && P > 0 && valid_K(K) && n_rows >= 0, "tip_em_workspace_bytes: bad arguments");
+    if (seg3_flag(flags)) {
+        *bytes = em_seg3_workspace_bytes(P, K, n_rows);
+        return 0;
+    }
     *bytes = uses_tuned(K, flags) ? em_tuned_workspace_bytes(P, K, seg_flag(flags))
                                   : (size_t)(n_rows < 1 ? 1 : n_rows) * sizeof(double);
     return 0;
@@ -59,9 +64,18 @@ extern "C" int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int
                 "tip_em_step: TIP_EM_FP32_COMPUTE exists for the K <= 10 kernels only, without FORCE_GENERIC / WITH_LOGLIK");
     TIP_REQUIRE(!seg_flag(flags) || !(flags & (TIP_EM_FORCE_GENERIC | TIP_EM_WITH_LOGLIK | TIP_EM_FP32_COMPUTE)),
                 "tip_em_step: TIP_EM_GENE_SEGMENTED cannot be combined with other mode flags");
+    TIP_REQUIRE(!seg3_flag(flags) || flags == TIP_EM_SLOT_SEGMENTED,
+                "tip_em_step: TIP_EM_SLOT_SEGMENTED cannot be combined with other mode flags");
     TIP_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * (size_t)tip_stats_len(P, K), st));
     if (n_rows == 0) return 0;
     const int4 *rows = reinterpret_cast<const int4 *>(d_rows);
+    if (seg3_flag(flags)) {
+        const size_t need = em_seg3_workspace_bytes(P, K, n_rows);
+        TIP_REQUIRE(d_ws != nullptr && ws_bytes >= need,
+                    "tip_em_step: the slot-segmented mode needs %zu bytes of workspace (got %zu), see tip_em_workspace_bytes",
+                    need, ws_bytes);
+        return launch_em_seg3(P, K, rows, n_rows, n_rows_r0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws), st);
+    }
     if (uses_tuned(K, flags)) {
         const size_t need = em_tuned_workspace_bytes(P, K, seg_flag(flags));
         TIP_REQUIRE(need == 0 || (d_ws != nullptr && ws_bytes >= need),

@@ -1,0 +1,724 @@
+// Slot-segmented E-step (TIP_EM_SLOT_SEGMENTED) for sm_100a: every theta statistic of Model.make_iteration
+// (TIP.py:1009-1011) and the p statistic (TIP.py:1012) are accumulated per RUN OF EQUAL GENE, in three sort orders of
+// the same links, so that no statistic is ever scattered with per-link atomics - a hub gene (a Kuzmin query gene
+// sits in tens of thousands of triplets) costs the same as any other.
+//
+// For a link (a, b, c) of rating r with count n:   d = eps + sum_abc th_a th_b th_c p_abc,r ,  s = n / d.
+//   pass A (rows ordered by slot-a gene g):  Z_g[b][c] = sum_a th_g[a] p[a][b][c][r]       (once per gene, seg3_prep_kernel)
+//                                            d = eps + sum_bc th_b[b] th_c[c] Z_g[b][c]    K^2 DFMA, lane = link
+//                                            s -> sbuf[position of the link in order a]
+//                                            M0_g[b][c] += s th_b[b] th_c[c]               K^2, tensor pipe (DMMA)
+//   pass B (rows ordered by slot-b gene g):  M1_g[a][c] += s th_a[a] th_c[c]               s read back from sbuf
+//   pass C (rows ordered by slot-c gene g):  M2_g[a][b] += s th_a[a] th_b[b]
+//   finish (once per iteration, per gene):   Ntheta[g][k] = th_g[k] * sum_{slot, r} sum_xy P_slot[r][k][xy] M_slot,r,g[xy]
+//                                            S[r][a][bc]  = sum_g th_g[a] M0_r,g[bc]        (npr = p * S)
+// A link costs 4 K^2 FMA instead of 3 K^3; what bounds the kernels is the gather of six theta rows per link from
+// L2 (6 x 96 bytes at K = 10) and instruction issue, not the FMA pipe.
+//
+// The M accumulation of a 32-link tile is a [K x 32] . [32 x K] product: it runs on the fp64 tensor path
+// (mma.sync.m8n8k4.f64, SASS DMMA - same pipe as DFMA, a quarter of the issue slots).  Operands are staged
+// TRANSPOSED in shared memory ([component][link], stride 36 doubles: fragment loads and the lane = link stores are
+// both conflict-free).  Accumulator fragments stay in registers across tiles and are flushed (red.global.add.f64)
+// only where the run of equal gene ends or the warp's chunk of tiles ends: atomics per iteration ~ K^2 x (#runs +
+// #chunks) instead of 2 K x #links.  Tiles are handed out dynamically (atomic chunk counter) to single-warp CTAs.
+#include <stdlib.h>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "tip_common.cuh"
+
+namespace tip {
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void red_add_f64_nz3(double *addr, double v)
+{
+    asm volatile("{ .reg .pred p; setp.neu.f64 p, %1, 0d0000000000000000; @p red.global.add.f64 [%0], %1; }" ::"l"(addr),
+                 "d"(v)
+                 : "memory");
+}
+
+template <int K>
+struct S3 {
+    static constexpr int KK = K * K;
+    static constexpr int NB = (K + 7) / 8;    // 8 x 8 accumulator blocks per dimension of M
+    static constexpr int NKG = (K + 3) / 4;   // k-steps of the d contraction
+    // stage row [th_x | th_y] of a link, stride == 4 (mod 16) doubles: the two fragment access patterns of this kernel -
+    // (row = link, col = component) and (row = component, col = link) - both hit every bank pair exactly twice
+    static constexpr int RS = ((2 * K + 11) / 16) * 16 + 4;
+    static constexpr size_t BUF_BYTES = (size_t)32 * RS * 8 + 32 * 8 + 32 * 16;   // stage | s | ids
+    static constexpr int UNIT = (K % 2 == 0) ? 2 : 1;                  // doubles per cp.async
+    static constexpr int U = K / UNIT;                                 // copies per theta row
+    static constexpr int LPI = (2 * U <= 32) ? 32 / (2 * U) : 0;       // whole links per gather instruction (0: flat mapping)
+    static constexpr int ITERS = LPI ? (32 + LPI - 1) / LPI : 2 * U;
+    static constexpr bool HOIST_Z = NB * NKG <= 12;                    // Z fragments of a run kept in registers
+};
+
+struct S3Args {
+    int P;
+    const int4 *rows;        // pass A: order a.  pass BC: order b followed by order c
+    int n_tiles;             // tiles this launch walks (tiles_per_order, or 2 x tiles_per_order)
+    int tiles_per_order;
+    int n_tiles_r0;          // rating-0 tiles of an order
+    int slot0;               // first slot of this launch (0 or 1)
+    const double *theta;
+    const double *Zg;        // [2][P][KK]            (pass A)
+    double *sbuf;            // [tiles_per_order * 32] (written by pass A, read by pass BC)
+    double *Mg;              // [3][2][P][KK]
+    unsigned *counter;       // chunk counter of this launch, zero on entry
+    int chunk;               // tiles per chunk
+    int tune;                // bit 0: gather through L1 (cp.async.ca) instead of L2 only (.cg)
+};
+
+__device__ __forceinline__ void cp_async_16_ca(void *smem_dst, const void *gmem_src)
+{
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+// 8 bytes, or zeros when src_bytes == 0 (the source is then not read)
+__device__ __forceinline__ void cp_async_8_zfill(void *smem_dst, const void *gmem_src, int src_bytes)
+{
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+
+// theta rows of the 32 links of a tile -> stage[link][th_x | th_y].  K even: 16-byte copies, whole links per warp
+// instruction (a row is never split over two instructions, so its three sectors are requested once)
+template <int K>
+__device__ __forceinline__ void s3_gather(const double *__restrict__ theta, const int4 *ids_sm, double *stage, int lane,
+                                          bool ca)
+{
+    using C = S3<K>;
+    const int *idw = reinterpret_cast<const int *>(ids_sm);
+    auto copy = [&](int l, int slot, int k0) {
+        const int g = idw[l * 4 + 1 + slot];
+        double *dst = stage + l * C::RS + slot * K + k0;
+        const double *src = theta + (int64_t)g * K + k0;
+        if (C::UNIT == 2) {
+            if (ca)
+                cp_async_16_ca(dst, src);
+            else
+                cp_async_16(dst, src);
+        } else {
+            cp_async_8(dst, src);
+        }
+    };
+    if constexpr (C::LPI > 0) {
+        const int sub = lane / (2 * C::U), rem = lane - sub * (2 * C::U);
+        const int slot = rem / C::U, k0 = (rem - slot * C::U) * C::UNIT;
+        if (sub < C::LPI) {
+#pragma unroll
+            for (int it = 0; it < C::ITERS; ++it) {
+                const int l = it * C::LPI + sub;
+                if (32 % C::LPI == 0 || l < 32) copy(l, slot, k0);
+            }
+        }
+    } else {
+#pragma unroll 4
+        for (int it = 0; it < C::ITERS; ++it) {
+            const int u = it * 32 + lane;
+            const int l = u / (2 * C::U), rem = u - l * (2 * C::U);
+            const int slot = rem / C::U;
+            copy(l, slot, (rem - slot * C::U) * C::UNIT);
+        }
+    }
+}
+
+// NST stage buffers: the gathers of the next NST - 1 tiles are in flight while a tile is computed
+template <int K, bool FIRST, int NST>
+__global__ void __launch_bounds__(32) seg3_pass_kernel(const S3Args a)
+{
+    using C = S3<K>;
+    constexpr int KK = C::KK, NB = C::NB, NKG = C::NKG, RS = C::RS, D = NST - 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x, li = lane & 3, ri = lane >> 2;
+    auto stage_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * C::BUF_BYTES); };
+    auto ids_of = [&](int b) { return reinterpret_cast<int4 *>(stage_of(b) + 32 * RS + 32); };
+    const bool ca = (a.tune & 1) != 0;
+
+    // fragment coordinates of this lane: component i*8 + ri of an 8 x 8 block (rows/cols >= K read as zero)
+    int xo[NB];
+    bool xv[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        xv[i] = i * 8 + ri < K;
+        xo[i] = xv[i] ? i * 8 + ri : 0;
+    }
+
+    double acc[NB][NB][2];
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    auto flush = [&](int mrow) {
+        double *dst = a.Mg + (int64_t)mrow * KK;
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int x = i * 8 + ri, y = j * 8 + 2 * li;
+                if (x < K && y < K) red_add_f64_nz3(dst + x * K + y, acc[i][j][0]);
+                if (x < K && y + 1 < K) red_add_f64_nz3(dst + x * K + y + 1, acc[i][j][1]);
+                acc[i][j][0] = acc[i][j][1] = 0.0;
+            }
+    };
+    auto mbase_of = [&](int tt) {
+        const int so = tt / a.tiles_per_order, tl = tt - so * a.tiles_per_order;
+        return ((a.slot0 + so) * 2 + (tl >= a.n_tiles_r0 ? 1 : 0)) * a.P;
+    };
+
+    // ---- tile sequence of this warp: chunks of consecutive tiles from an atomic counter, fetched one chunk ahead ----
+    int gen_t = 0, gen_end = 0;
+    bool gen_done = false;
+    unsigned pend = 0;
+    if (lane == 0) pend = atomicAdd(a.counter, 1u);
+    auto next_tile = [&]() -> int {
+        if (gen_t < gen_end) return gen_t++;
+        if (gen_done) return -1;
+        const unsigned c = __shfl_sync(0xffffffffu, pend, 0);
+        const long long t0 = (long long)c * a.chunk;
+        if (t0 >= a.n_tiles) {
+            gen_done = true;
+            return -1;
+        }
+        gen_t = (int)t0;
+        gen_end = (t0 + a.chunk < a.n_tiles) ? (int)t0 + a.chunk : a.n_tiles;
+        if (lane == 0) pend = atomicAdd(a.counter, 1u);
+        return gen_t++;
+    };
+    auto issue_gather = [&](int buf, const int4 &me) {
+        int4 *ids = ids_of(buf);
+        double *st = stage_of(buf);
+        ids[lane] = me;
+        __syncwarp();
+        s3_gather<K>(a.theta, ids, st, lane, ca);
+        if constexpr (!FIRST) cp_async_8_zfill(st + 32 * RS + lane, a.sbuf + (me.w >= 0 ? me.w : 0), me.w >= 0 ? 8 : 0);
+    };
+
+    int tq[NST];  // tq[0]: tile computed this iteration; tq[1 .. D-1]: gathers in flight; tq[D]: rows in me_pend
+    int4 me_pend = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        tq[j] = next_tile();
+        if (tq[j] >= 0) issue_gather(j, a.rows[(int64_t)tq[j] * 32 + lane]);
+        cp_async_commit();
+    }
+    tq[D] = next_tile();
+    if (tq[D] >= 0) me_pend = a.rows[(int64_t)tq[D] * 32 + lane];
+
+    int cb = 0;    // buffer of tq[0]
+    int cur = -1;  // run the accumulators belong to (-1: none)
+    int zcur = -1; // run whose Z fragments are in registers
+    double zf[C::HOIST_Z ? NB : 1][C::HOIST_Z ? NKG : 1];
+    (void)zcur; (void)zf;
+
+    while (tq[0] >= 0) {
+        // ---- A: gather of the tile D ahead; B: rows of the tile D + 1 ahead ----
+        {
+            int gb = cb + D;
+            if (gb >= NST) gb -= NST;
+            if (tq[D] >= 0) issue_gather(gb, me_pend);
+            cp_async_commit();
+        }
+        const int tn = next_tile();
+        if (tn >= 0) me_pend = a.rows[(int64_t)tn * 32 + lane];
+        cp_async_wait<D>();
+        __syncwarp();
+
+        const int t = tq[0];
+        double *st = stage_of(cb);
+        double *ssm = st + 32 * RS;
+        const int4 *ids = ids_of(cb);
+        const int mrow = mbase_of(t) + ids[lane].x;
+        int prev = __shfl_up_sync(0xffffffffu, mrow, 1);
+        if (cur < 0) cur = __shfl_sync(0xffffffffu, mrow, 0);
+        if (lane == 0) prev = cur;
+        const unsigned bm = __ballot_sync(0xffffffffu, mrow != prev);  // bit l: link l starts a new run
+
+        if constexpr (FIRST) {
+            // ---- Y[link][b] = sum_c th_c[c] Z_g[b][c], one masked tensor product per run of equal gene ----
+            double Y[4][NB][2];
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb)
+#pragma unroll
+                for (int j = 0; j < NB; ++j) Y[rb][j][0] = Y[rb][j][1] = 0.0;
+            int l0 = 0;
+            while (l0 < 32) {
+                const unsigned rest = (l0 < 31) ? (bm & ~((2u << l0) - 1u)) : 0u;  // run starts after l0
+                const int l1 = rest ? __ffs(rest) - 1 : 32;
+                const int mseg = __shfl_sync(0xffffffffu, mrow, l0);
+                const double *Zr = a.Zg + (int64_t)mseg * KK;
+                if constexpr (C::HOIST_Z) {
+                    if (mseg != zcur) {
+#pragma unroll
+                        for (int j = 0; j < NB; ++j)
+#pragma unroll
+                            for (int kg = 0; kg < NKG; ++kg)
+                                zf[j][kg] = (xv[j] && 4 * kg + li < K) ? __ldg(Zr + xo[j] * K + 4 * kg + li) : 0.0;
+                        zcur = mseg;
+                    }
+                }
+#pragma unroll
+                for (int rb = 0; rb < 4; ++rb) {
+                    if (rb * 8 < l1 && rb * 8 + 8 > l0) {
+                        const int lr = rb * 8 + ri;
+                        const bool in = lr >= l0 && lr < l1;
+#pragma unroll
+                        for (int kg = 0; kg < NKG; ++kg) {
+                            const double av = (in && 4 * kg + li < K) ? st[lr * RS + K + 4 * kg + li] : 0.0;
+#pragma unroll
+                            for (int j = 0; j < NB; ++j) {
+                                double zv;
+                                if constexpr (C::HOIST_Z)
+                                    zv = zf[j][kg];
+                                else
+                                    zv = (xv[j] && 4 * kg + li < K) ? __ldg(Zr + xo[j] * K + 4 * kg + li) : 0.0;
+                                dmma884(Y[rb][j][0], Y[rb][j][1], av, zv);
+                            }
+                        }
+                    }
+                }
+                l0 = l1;
+            }
+            // ---- d = eps + sum_b th_b[b] Y[b];  s = count / d for link li * 8 + ri ----
+            double dsel = 1.0;
+#pragma unroll
+            for (int rb = 0; rb < 4; ++rb) {
+                double part = 0.0;
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const int b0 = j * 8 + 2 * li;
+                    if (b0 < K) {  // (same for every use of this lane: no divergence cost beyond predication)
+                        const double2 tb = *reinterpret_cast<const double2 *>(st + (rb * 8 + ri) * RS + b0);
+                        part = fma(tb.x, Y[rb][j][0], part);
+                        if (b0 + 1 < K) part = fma(tb.y, Y[rb][j][1], part);
+                    }
+                }
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                if (li == rb) dsel = TIP_EPS + part;
+            }
+            const int L = li * 8 + ri;
+            // 1/d: fp32 reciprocal seed and three Newton steps (d lies in [1e-10, ~1]; last-ulp accuracy, see tip_em.cu)
+            double rd = (double)__frcp_rn((float)dsel);
+            rd = rd * fma(-dsel, rd, 2.0);
+            rd = rd * fma(-dsel, rd, 2.0);
+            rd = rd * fma(-dsel, rd, 2.0);
+            const double s = (double)row_count(ids[L].w) * rd;
+            ssm[L] = s;
+            a.sbuf[(int64_t)t * 32 + L] = s;
+            __syncwarp();
+        }
+
+        // ---- M += (s th_x)^T . th_y over the runs of equal gene in this tile ----
+#pragma unroll 2
+        for (int ks = 0; ks < 8; ++ks) {
+            const unsigned nib = (bm >> (4 * ks)) & 15u;
+            const double *lrow = st + (4 * ks + li) * RS;
+            const double sv = ssm[4 * ks + li];
+            double av[NB], bv[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                av[i] = xv[i] ? lrow[xo[i]] * sv : 0.0;
+                bv[i] = xv[i] ? lrow[K + xo[i]] : 0.0;
+            }
+            if (nib == 0) {
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+            } else {
+                // a run ends inside these four links: one masked product per segment
+                int j0 = 0;
+                while (j0 < 4) {
+                    if ((nib >> j0) & 1u) {
+                        flush(cur);
+                        cur = __shfl_sync(0xffffffffu, mrow, 4 * ks + j0);
+                    }
+                    const unsigned higher = nib >> (j0 + 1);
+                    const int len = higher ? __ffs(higher) : 4 - j0;
+                    const bool mine = li >= j0 && li < j0 + len;
+#pragma unroll
+                    for (int i = 0; i < NB; ++i)
+#pragma unroll
+                        for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], mine ? av[i] : 0.0, bv[j]);
+                    j0 += len;
+                }
+            }
+        }
+        if (tq[1 % NST] != t + 1) {  // the warp's chunk ends here
+            flush(cur);
+            cur = -1;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < D; ++j) tq[j] = tq[j + 1];
+        tq[D] = tn;
+        if (++cb == NST) cb = 0;
+    }
+}
+
+// Z[r][g][b][c] = sum_a theta[g][a] p[a][b][c][r]  (one CTA per group of genes, p staged in shared memory), and the three
+// orientations of p the finish contracts with:
+//   PT[slot][r][k][e]:  slot 0: k = a, e = (b, c);  slot 1: k = b, e = (a, c);  slot 2: k = c, e = (a, b)
+constexpr int kPrepGenes = 8;
+__global__ void __launch_bounds__(256) seg3_prep_kernel(int P, int K, const double *__restrict__ theta,
+                                                        const double *__restrict__ p, double *__restrict__ Zg,
+                                                        double *__restrict__ PT)
+{
+    extern __shared__ double psm[];  // [2][K^3]  p[r][a][bc]   (only when it fits: K <= 20)
+    const int KK = K * K, K3 = KK * K;
+    const bool staged = K <= 20;
+    if (staged) {
+        for (int e = threadIdx.x; e < 2 * K3; e += blockDim.x) psm[(e & 1) * K3 + (e >> 1)] = __ldg(p + e);
+        __syncthreads();
+    }
+    const int g0 = blockIdx.x * kPrepGenes;
+    const int n = 2 * kPrepGenes * KK;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int gi = e / (2 * KK), rem = e - gi * (2 * KK), r = rem / KK, bc = rem - r * KK;
+        const int g = g0 + gi;
+        if (g >= P) break;
+        const double *th = theta + (int64_t)g * K;
+        double z = 0.0;
+        if (staged)
+            for (int q = 0; q < K; ++q) z = fma(__ldg(th + q), psm[r * K3 + q * KK + bc], z);
+        else
+            for (int q = 0; q < K; ++q) z = fma(__ldg(th + q), __ldg(p + ((int64_t)q * KK + bc) * 2 + r), z);
+        Zg[((int64_t)r * P + g) * KK + bc] = z;
+    }
+    // the transposed copies of p: spread over the CTAs
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < 6 * K3; f += gridDim.x * blockDim.x) {
+        const int slot = f / (2 * K3), rem = f - slot * 2 * K3;
+        const int r = rem / K3, ke = rem - r * K3, k = ke / KK, xy = ke - k * KK, x = xy / K, y = xy - x * K;
+        int i, j, l;
+        if (slot == 0) { i = k; j = x; l = y; }
+        else if (slot == 1) { i = x; j = k; l = y; }
+        else { i = x; j = y; l = k; }
+        PT[f] = __ldg(p + (((int64_t)i * K + j) * K + l) * 2 + r);
+    }
+}
+
+// Per-gene finish.  Warp tasks, both as small fp64 tensor products straight out of L2 (no shared memory):
+//   kind 1, task (group of 8 genes, slot):  Ntheta[g][k] += th_g[k] * sum_r sum_e M_slot,r,g[e] PT[slot][r][k][e]
+//   kind 2, task (r, block of 8 (b,c) cells, chunk of genes):  S[r][a][bc] += sum_g th_g[a] M_0,r,g[bc]
+constexpr int kFin3Threads = 256;
+constexpr int kFin3GeneChunk = 96;  // genes per kind-2 task
+
+template <int K>
+__global__ void __launch_bounds__(kFin3Threads) seg3_finish_kernel(int P, const double *__restrict__ theta,
+                                                                     const double *__restrict__ PT,
+                                                                     const double *__restrict__ Mg, double *__restrict__ stats)
+{
+    constexpr int KK = K * K, K3 = KK * K, NB = (K + 7) / 8, NBC = (KK + 7) / 8;
+    const int lane = threadIdx.x & 31, li = lane & 3, ri = lane >> 2;
+    const int wt = blockIdx.x * (kFin3Threads / 32) + (threadIdx.x >> 5);
+    const int n_groups = (P + 7) / 8, n_kind1 = n_groups * 3;
+    const int n_chunks = (P + kFin3GeneChunk - 1) / kFin3GeneChunk, n_kind2 = 2 * NBC * n_chunks;
+    if (wt < n_kind1) {
+        const int slot = wt % 3, g = (wt / 3) * 8 + ri;
+        const bool gv = g < P;
+        double c[NB][2];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) c[i][0] = c[i][1] = 0.0;
+        for (int r = 0; r < 2; ++r) {
+            const double *Mrow = Mg + ((int64_t)(slot * 2 + r) * P + (gv ? g : 0)) * KK;
+            const double *Pr = PT + (int64_t)(slot * 2 + r) * K3;
+#pragma unroll 5
+            for (int e0 = 0; e0 < KK; e0 += 4) {
+                const int e = e0 + li;
+                const bool ev = e < KK;
+                const double av = (gv && ev) ? __ldg(Mrow + e) : 0.0;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int k = i * 8 + ri;
+                    const double bv = (k < K && ev) ? __ldg(Pr + k * KK + e) : 0.0;
+                    dmma884(c[i][0], c[i][1], av, bv);
+                }
+            }
+        }
+        if (gv) {
+#pragma unroll
+            for (int i = 0; i < NB; ++i)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = i * 8 + 2 * li + h;
+                    if (k < K) red_add_f64_nz3(stats + (int64_t)g * K + k, __ldg(theta + (int64_t)g * K + k) * c[i][h]);
+                }
+        }
+    } else if (wt < n_kind1 + n_kind2) {
+        const int w2 = wt - n_kind1;
+        const int chunk = w2 / (2 * NBC), rem = w2 - chunk * (2 * NBC), r = rem / NBC, bcb = rem - r * NBC;
+        const int g_lo = chunk * kFin3GeneChunk, g_hi = (g_lo + kFin3GeneChunk < P) ? g_lo + kFin3GeneChunk : P;
+        const int bc = bcb * 8 + ri;
+        const double *Mr = Mg + (int64_t)r * P * KK;  // slot 0
+        double c[NB][2];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) c[i][0] = c[i][1] = 0.0;
+#pragma unroll 4
+        for (int g0 = g_lo; g0 < g_hi; g0 += 4) {
+            const int g = g0 + li;
+            const bool gv = g < g_hi;
+            const double bv = (gv && bc < KK) ? __ldg(Mr + (int64_t)g * KK + bc) : 0.0;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const int al = i * 8 + ri;
+                const double av = (gv && al < K) ? __ldg(theta + (int64_t)g * K + al) : 0.0;
+                dmma884(c[i][0], c[i][1], av, bv);
+            }
+        }
+        double *S = stats + stats_off_S(P, K) + (int64_t)r * K3;
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int al = i * 8 + ri, cell = bcb * 8 + 2 * li + h;
+                if (al < K && cell < KK) red_add_f64_nz3(S + (int64_t)al * KK + cell, c[i][h]);
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace:  M[3][2][P][KK] | counters (32 doubles) | Z[2][P][ZK] | PT[3][2][K^3] | sbuf[n_rows]
+// ---------------------------------------------------------------------------------------------
+struct S3Layout {
+    size_t off_M, off_cnt, off_Z, off_PT, off_s, total;  // in doubles
+};
+static S3Layout s3_layout(int P, int K, int64_t n_rows)
+{
+    const size_t KK = (size_t)K * K;
+    S3Layout l;
+    l.off_M = 0;
+    l.off_cnt = 6 * (size_t)P * KK;
+    l.off_Z = l.off_cnt + 32;
+    l.off_PT = l.off_Z + 2 * (size_t)P * KK;
+    l.off_PT = (l.off_PT + 1) / 2 * 2;
+    l.off_s = l.off_PT + 6 * KK * K;
+    l.off_s = (l.off_s + 1) / 2 * 2;
+    l.total = l.off_s + (size_t)(n_rows < 32 ? 32 : n_rows);
+    return l;
+}
+
+size_t em_seg3_workspace_bytes(int P, int K, int64_t n_rows) { return s3_layout(P, K, n_rows).total * sizeof(double); }
+
+static int s3_tune()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TIP_SEG3_TUNE");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+static int s3_chunk_tiles()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TIP_SEG3_CHUNK");
+        v = e ? atoi(e) : 2;
+        if (v < 1) v = 1;
+    }
+    return v;
+}
+
+static int s3_stages()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TIP_SEG3_STAGES");
+        v = e ? atoi(e) : 2;
+        if (v != 2 && v != 3) v = 2;
+    }
+    return v;
+}
+
+template <int K, bool FIRST, int NST>
+static int s3_launch_pass_n(const S3Args &a, cudaStream_t st)
+{
+    using C = S3<K>;
+    constexpr size_t smem = C::BUF_BYTES * NST;
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        TIP_CHECK_CUDA(cudaFuncSetAttribute(seg3_pass_kernel<K, FIRST, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TIP_CHECK_CUDA(cudaFuncSetAttribute(seg3_pass_kernel<K, FIRST, NST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            cudaSharedmemCarveoutMaxShared));
+        int nb = 0;
+        TIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seg3_pass_kernel<K, FIRST, NST>, 32, smem));
+        TIP_REQUIRE(nb >= 1, "seg3_pass_kernel<%d> does not fit on an SM (smem %zu)", K, smem);
+        blocks_per_sm = nb;
+    }
+    const int64_t chunks = ((int64_t)a.n_tiles + a.chunk - 1) / a.chunk;
+    const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+    int grid = (int)(chunks < cap ? chunks : cap);
+    if (grid < 1) grid = 1;
+    seg3_pass_kernel<K, FIRST, NST><<<grid, 32, smem, st>>>(a);
+    TIP_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int K, bool FIRST>
+static int s3_launch_pass(const S3Args &a, cudaStream_t st)
+{
+    if (s3_stages() == 3) return s3_launch_pass_n<K, FIRST, 3>(a, st);
+    return s3_launch_pass_n<K, FIRST, 2>(a, st);
+}
+
+template <int K>
+static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
+                            double *stats, double *ws, cudaStream_t st)
+{
+    const S3Layout l = s3_layout(P, K, n_rows);
+    const int KK = K * K;
+    TIP_REQUIRE(n_rows / 32 < (1ll << 29), "tip_em_step: too many tiles in one shard for the slot-segmented kernels");
+    // M and the chunk counters start from zero
+    TIP_CHECK_CUDA(cudaMemsetAsync(ws + l.off_M, 0, sizeof(double) * (l.off_cnt + 32), st));
+    {
+        const size_t smem = K <= 20 ? sizeof(double) * 2 * KK * K : 0;
+        static bool attr = false;
+        if (!attr && smem > 48 * 1024) {
+            TIP_CHECK_CUDA(cudaFuncSetAttribute(seg3_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            attr = true;
+        }
+        seg3_prep_kernel<<<(P + kPrepGenes - 1) / kPrepGenes, 256, smem, st>>>(P, K, theta, p, ws + l.off_Z, ws + l.off_PT);
+        TIP_CHECK_CUDA(cudaGetLastError());
+    }
+    S3Args a;
+    a.P = P;
+    a.rows = rows;
+    a.tiles_per_order = (int)(n_rows / 32);
+    a.n_tiles_r0 = (int)(n_rows_r0 / 32);
+    a.theta = theta;
+    a.Zg = ws + l.off_Z;
+    a.sbuf = ws + l.off_s;
+    a.Mg = ws + l.off_M;
+    a.chunk = s3_chunk_tiles();
+    a.tune = s3_tune();
+    a.n_tiles = a.tiles_per_order;
+    a.slot0 = 0;
+    a.counter = reinterpret_cast<unsigned *>(ws + l.off_cnt);
+    int rc = s3_launch_pass<K, true>(a, st);
+    if (rc) return rc;
+    a.rows = rows + n_rows;
+    a.n_tiles = 2 * a.tiles_per_order;
+    a.slot0 = 1;
+    a.counter = reinterpret_cast<unsigned *>(ws + l.off_cnt) + 4;
+    rc = s3_launch_pass<K, false>(a, st);
+    if (rc) return rc;
+    {
+        constexpr int NBC = (K * K + 7) / 8;
+        const int n_tasks = ((P + 7) / 8) * 3 + 2 * NBC * ((P + kFin3GeneChunk - 1) / kFin3GeneChunk);
+        const int wpc = kFin3Threads / 32;
+        seg3_finish_kernel<K><<<(n_tasks + wpc - 1) / wpc, kFin3Threads, 0, st>>>(P, theta, ws + l.off_PT, ws + l.off_M, stats);
+        TIP_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// rows: order a | order b | order c, n_rows rows each (tip_order_rows); stats zeroed by the caller
+int launch_em_seg3(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
+                   double *stats, double *ws, cudaStream_t st)
+{
+    switch (K) {
+#define TIP_S3_CASE(k) \
+    case k: return launch_em_seg3_k<k>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st);
+        TIP_S3_CASE(1) TIP_S3_CASE(2) TIP_S3_CASE(3) TIP_S3_CASE(4) TIP_S3_CASE(5) TIP_S3_CASE(6) TIP_S3_CASE(7) TIP_S3_CASE(8)
+        TIP_S3_CASE(9) TIP_S3_CASE(10) TIP_S3_CASE(11) TIP_S3_CASE(12) TIP_S3_CASE(13) TIP_S3_CASE(14) TIP_S3_CASE(15)
+        TIP_S3_CASE(16) TIP_S3_CASE(17) TIP_S3_CASE(18) TIP_S3_CASE(19) TIP_S3_CASE(20) TIP_S3_CASE(21) TIP_S3_CASE(22)
+        TIP_S3_CASE(23) TIP_S3_CASE(24) TIP_S3_CASE(25) TIP_S3_CASE(26) TIP_S3_CASE(27) TIP_S3_CASE(28) TIP_S3_CASE(29)
+        TIP_S3_CASE(30) TIP_S3_CASE(31) TIP_S3_CASE(32)
+#undef TIP_S3_CASE
+        default: set_error("launch_em_seg3: K = %d out of range", K); return -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tip_order_rows: the order-b and order-c copies of the packed rows
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned kOrderPadBit = 1u << 20, kOrderRatingShift = 21;
+
+__global__ void order_keys_kernel(const int4 *__restrict__ rows, int64_t n_rows, int64_t n_rows_r0, int slot,
+                                  unsigned *__restrict__ keys, int32_t *__restrict__ vals)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+        const int4 v = rows[i];
+        const unsigned r = i >= n_rows_r0 ? 1u : 0u;
+        const unsigned g = (unsigned)(slot == 1 ? v.y : v.z);
+        keys[i] = (r << kOrderRatingShift) | (row_count(v.w) > 0 ? g : kOrderPadBit);
+        vals[i] = (int32_t)i;
+    }
+}
+
+__global__ void order_emit_kernel(const int4 *__restrict__ rows, const int32_t *__restrict__ vals, int64_t n_rows, int slot,
+                                  int4 *__restrict__ out)
+{
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_rows; j += (int64_t)gridDim.x * blockDim.x) {
+        const int src = vals[j];
+        const int4 v = rows[src];
+        int4 o = make_int4(0, 0, 0, -1);
+        if (row_count(v.w) > 0) o = slot == 1 ? make_int4(v.y, v.x, v.z, src) : make_int4(v.z, v.x, v.y, src);
+        out[j] = o;
+    }
+}
+
+static size_t order_layout(int64_t n, size_t *o_ki, size_t *o_ko, size_t *o_vi, size_t *o_vo, size_t *o_cub, size_t *cub_bytes)
+{
+    size_t cb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cb, (const unsigned *)nullptr, (unsigned *)nullptr, (const int32_t *)nullptr,
+                                    (int32_t *)nullptr, n, 0, 22, (cudaStream_t)0);
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t off = 0;
+    *o_ki = off; off += al((size_t)n * 4);
+    *o_ko = off; off += al((size_t)n * 4);
+    *o_vi = off; off += al((size_t)n * 4);
+    *o_vo = off; off += al((size_t)n * 4);
+    *o_cub = off; off += al(cb);
+    *cub_bytes = cb;
+    return off + 256;
+}
+
+}  // namespace tip
+
+using namespace tip;
+
+extern "C" int tip_order_rows_workspace_bytes(int64_t n_rows, size_t *bytes)
+{
+    TIP_REQUIRE(n_rows >= 0 && bytes != nullptr, "tip_order_rows_workspace_bytes: bad arguments");
+    size_t a, b, c, d, e, f;
+    *bytes = order_layout(n_rows < 32 ? 32 : n_rows, &a, &b, &c, &d, &e, &f);
+    return 0;
+}
+
+extern "C" int tip_order_rows(const void *d_rows, int64_t n_rows, int64_t n_rows_r0, void *d_ws, size_t ws_bytes,
+                              void *d_rows_bc, void *stream)
+{
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TIP_REQUIRE(n_rows >= 0 && n_rows % 32 == 0 && n_rows_r0 >= 0 && n_rows_r0 <= n_rows && n_rows < (1ll << 31),
+                "tip_order_rows: n_rows (%lld) must be a multiple of 32 below 2^31", (long long)n_rows);
+    if (n_rows == 0) return 0;
+    TIP_REQUIRE(d_rows && d_rows_bc && d_ws, "tip_order_rows: null pointer");
+    size_t o_ki, o_ko, o_vi, o_vo, o_cub, cub_bytes;
+    const size_t need = order_layout(n_rows, &o_ki, &o_ko, &o_vi, &o_vo, &o_cub, &cub_bytes);
+    TIP_REQUIRE(ws_bytes >= need, "tip_order_rows: workspace too small (%zu < %zu)", ws_bytes, need);
+    char *base = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(d_ws) + 255) / 256 * 256);
+    unsigned *ki = reinterpret_cast<unsigned *>(base + o_ki), *ko = reinterpret_cast<unsigned *>(base + o_ko);
+    int32_t *vi = reinterpret_cast<int32_t *>(base + o_vi), *vo = reinterpret_cast<int32_t *>(base + o_vo);
+    const int4 *rows = reinterpret_cast<const int4 *>(d_rows);
+    int4 *out = reinterpret_cast<int4 *>(d_rows_bc);
+    const int64_t want = (n_rows + 255) / 256;
+    const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
+    for (int slot = 1; slot <= 2; ++slot) {
+        order_keys_kernel<<<grid, 256, 0, st>>>(rows, n_rows, n_rows_r0, slot, ki, vi);
+        TIP_CHECK_CUDA(cudaGetLastError());
+        size_t cb = cub_bytes;
+        TIP_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(base + o_cub, cb, ki, ko, vi, vo, n_rows, 0, 22, st));
+        order_emit_kernel<<<grid, 256, 0, st>>>(rows, vo, n_rows, slot, out + (slot - 1) * n_rows);
+        TIP_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}

@@ -28,10 +28,17 @@ class PackedLinks:
 
     def __init__(self, rows, n_rows, n_rows_r0, n_real, deg):
         self.rows, self.n_rows, self.n_rows_r0, self.n_real, self.deg = rows, n_rows, n_rows_r0, n_real, deg
+        self.rows3 = None     # slot-a | slot-b | slot-c orders back to back (tip_order_rows); rows is then its first third
+
+
+def default_flags(K: int) -> int:
+    """E-step formulation used when the caller does not choose one: the slot-segmented kernels (4K^2 FMA per
+    link, no per-link atomics, indifferent to hub genes) wherever they are the fastest correct path."""
+    return _cabi.TIP_EM_SLOT_SEGMENTED if K >= 5 else _cabi.TIP_EM_DEFAULT
 
 
 class EMEngine:
-    def __init__(self, P: int, K: int, device=None, group=None, flags: int = _cabi.TIP_EM_DEFAULT,
+    def __init__(self, P: int, K: int, device=None, group=None, flags: int | None = None,
                  exchange: str = "peer"):
         if not torch.cuda.is_available():
             raise _cabi.TipLibraryError("no CUDA device: trigenicinteractionpredictor_b200 has no CPU path")
@@ -39,7 +46,7 @@ class EMEngine:
         self.P, self.K = int(P), int(K)
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.group = group
-        self.flags = int(flags)
+        self.flags = default_flags(int(K)) if flags is None else int(flags)
         # group=None means "this process alone" (NOT torch.distributed's default group): link shards are opt-in
         self.world = _dist.world_size(group) if group is not None else 1
         self.n_stats = int(self.lib.tip_stats_len(self.P, self.K))
@@ -91,10 +98,27 @@ class EMEngine:
             rows = rows[: n_rows.value].clone() if n_rows.value < rows.shape[0] else rows
         return PackedLinks(rows, int(n_rows.value), int(part[0]), int(part[2]), deg)
 
+    def order_rows(self, links: PackedLinks):
+        """tip_order_rows: append the slot-b and slot-c orders of the packed rows (TIP_EM_SLOT_SEGMENTED)."""
+        n = links.n_rows
+        with torch.cuda.device(self.device):
+            nb = ctypes.c_size_t(0)
+            _cabi.check(self.lib.tip_order_rows_workspace_bytes(n, ctypes.byref(nb)), "tip_order_rows_workspace_bytes")
+            ws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+            rows3 = torch.empty((3 * n, 4), dtype=torch.int32, device=self.device)
+            rows3[:n].copy_(links.rows[:n])
+            _cabi.check(self.lib.tip_order_rows(_ptr(rows3), n, links.n_rows_r0, _ptr(ws), nb.value,
+                                                ctypes.c_void_p(rows3.data_ptr() + n * 16), self._stream()), "tip_order_rows")
+            self.launches += 4
+            torch.cuda.current_stream(self.device).synchronize()
+        links.rows3, links.rows = rows3, rows3[:n]
+
     def set_train_links(self, g1, g2, g3, n0, n1, global_deg=None):
         """This rank's shard of the training links.  `deg` (distinct links per gene, TIP.py:986-994) is
         summed over shards unless the caller supplies the global vector."""
         self.train = self.pack(g1, g2, g3, n0, n1, want_deg=True)
+        if self.flags & _cabi.TIP_EM_SLOT_SEGMENTED:
+            self.order_rows(self.train)
         if global_deg is not None:
             self.train.deg = self._as_dev_i32(global_deg)
         elif self.world > 1:
@@ -136,10 +160,14 @@ class EMEngine:
         """E-step statistics of this rank's rows into `stats` (default self.stats); no normalisation."""
         t = self.train
         stats = self.stats if stats is None else stats
-        _cabi.check(self.lib.tip_em_step(self.P, self.K, _ptr(t.rows), t.n_rows, t.n_rows_r0, _ptr(self.theta),
+        seg3 = bool(self.flags & _cabi.TIP_EM_SLOT_SEGMENTED)
+        _cabi.check(self.lib.tip_em_step(self.P, self.K, _ptr(t.rows3 if seg3 else t.rows), t.n_rows, t.n_rows_r0, _ptr(self.theta),
                                          _ptr(self.p), _ptr(stats), _ptr(self.em_ws), self.em_ws_bytes,
                                          self.flags, self._stream()), "tip_em_step")
-        self.launches += 3 if (self.K > 4 and not (self.flags & _cabi.TIP_EM_FORCE_GENERIC)) else 2
+        if self.flags & _cabi.TIP_EM_SLOT_SEGMENTED:
+            self.launches += 4                      # prep, pass A, pass B+C, finish
+        else:
+            self.launches += 3 if (self.K > 4 and not (self.flags & _cabi.TIP_EM_FORCE_GENERIC)) else 2
 
     def em_step_host_rows(self, h_rows: torch.Tensor, compact: bool, stats=None):
         """E-step of this rank's rows read from PINNED HOST memory (16-byte rows, or the 8-byte rows of
@@ -253,7 +281,8 @@ class EMEngine:
         if links is None:
             raise ValueError("no %s links set" % which)
         _cabi.check(self.lib.tip_loglik(self.P, self.K, _ptr(links.rows), links.n_rows, links.n_rows_r0, _ptr(self.theta),
-                                        _ptr(self.p), _ptr(self.ll_out), _ptr(self.ll_ws), self.flags, self._stream()),
+                                        _ptr(self.p), _ptr(self.ll_out), _ptr(self.ll_ws),
+                                        self.flags & _cabi.TIP_EM_FORCE_GENERIC, self._stream()),
                     "tip_loglik")
         self.launches += 2 if (self.K <= 10 and not (self.flags & _cabi.TIP_EM_FORCE_GENERIC)) else 1
         if self.world > 1 and which == "train":
