@@ -57,6 +57,10 @@ extern "C" {
                                    equal gene, in three sort orders of the links (4K^2 FMA per link, no per-link atomics:
                                    hub genes cost nothing extra).  d_rows then holds the three orders back to back, n_rows
                                    rows each: the packed rows, then tip_order_rows' output */
+#define TIP_EM_GATHER_L1 64u     /* with TIP_EM_SLOT_SEGMENTED: gather the theta rows through L1 (cp.async.ca) instead of L2
+                                   only.  For hub-shaped links (a few genes in most triplets): the hub rows then stay in
+                                   L1 instead of being requested from a handful of L2 slices by every SM (measured 0.31 ->
+                                   0.24 ms at 800k Kuzmin-shaped links); costs ~4 % on uniform links */
 #define TIP_EM_WITH_LOGLIK 4u   /* also accumulate the log-likelihood by-product (last stats slot); off by
                                    default because the log costs ~2 % of a K=10 step and the training loop only
                                    needs the likelihood every `fcheck` iterations (tip_loglik) */

@@ -7,6 +7,7 @@ import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+kname = sys.argv[3] if len(sys.argv) > 3 else None     # substring of the kernel whose SASS table is printed
 
 
 def page(name, extra=()):
@@ -23,7 +24,14 @@ want = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "smsp__cycles_active
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors_op_red.sum", "l1tex__t_sector_hit_rate.pct",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed_pipe_uniform.sum",
-        "idc__request_cycles_active.avg.pct_of_peak_sustained_active", "smsp__pcsamp_sample_buffers.sum"]
+        "idc__request_cycles_active.avg.pct_of_peak_sustained_active", "smsp__pcsamp_sample_buffers.sum",
+        "lts__t_sectors_srcunit_tex.sum", "lts__t_sectors_srcunit_tex.sum.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "derived__lts__lts2xbar_bytes.sum.per_second",
+        "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed"]
+if "Kernel Name" in hdr:
+    print("kernels:", [r[hdr.index("Kernel Name")][:48] for r in data])
 for w in want:
     if w in hdr:
         i = hdr.index(w)
@@ -34,7 +42,14 @@ for h in hdr:
         print("%-70s %-12s %s" % (h, units[i], [r[i] for r in data]))
 
 src = page("source", ["--print-source", "sass"])
-hi = [i for i, r in enumerate(src) if r and r[0] == "Address"][0]
+his = [i for i, r in enumerate(src) if r and r[0] == "Address"]
+hi = his[0]
+if kname:
+    for i in his:
+        if i > 0 and len(src[i - 1]) > 1 and kname in src[i - 1][1]:
+            hi = i
+            break
+print("SASS table of:", src[hi - 1][1][:80] if hi > 0 and len(src[hi - 1]) > 1 else "?")
 sh = src[hi]
 col = {h: i for i, h in enumerate(sh)}
 rows, seen = [], set()

@@ -23,6 +23,7 @@ TIP_EM_WITH_LOGLIK = 4
 TIP_EM_GENE_SEGMENTED = 8
 TIP_ROWS_COMPACT8 = 16
 TIP_EM_SLOT_SEGMENTED = 32
+TIP_EM_GATHER_L1 = 64
 
 # name -> (restype, argtypes); must list every function include/tip.h declares (tests check this)
 SIGNATURES = {

@@ -64,8 +64,9 @@ extern "C" int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int
                 "tip_em_step: TIP_EM_FP32_COMPUTE exists for the K <= 10 kernels only, without FORCE_GENERIC / WITH_LOGLIK");
     TIP_REQUIRE(!seg_flag(flags) || !(flags & (TIP_EM_FORCE_GENERIC | TIP_EM_WITH_LOGLIK | TIP_EM_FP32_COMPUTE)),
                 "tip_em_step: TIP_EM_GENE_SEGMENTED cannot be combined with other mode flags");
-    TIP_REQUIRE(!seg3_flag(flags) || flags == TIP_EM_SLOT_SEGMENTED,
-                "tip_em_step: TIP_EM_SLOT_SEGMENTED cannot be combined with other mode flags");
+    TIP_REQUIRE(!seg3_flag(flags) || (flags & ~(TIP_EM_SLOT_SEGMENTED | TIP_EM_GATHER_L1)) == 0,
+                "tip_em_step: TIP_EM_SLOT_SEGMENTED combines with TIP_EM_GATHER_L1 only");
+    TIP_REQUIRE(seg3_flag(flags) || !(flags & TIP_EM_GATHER_L1), "tip_em_step: TIP_EM_GATHER_L1 needs TIP_EM_SLOT_SEGMENTED");
     TIP_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * (size_t)tip_stats_len(P, K), st));
     if (n_rows == 0) return 0;
     const int4 *rows = reinterpret_cast<const int4 *>(d_rows);
@@ -74,7 +75,8 @@ extern "C" int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int
         TIP_REQUIRE(d_ws != nullptr && ws_bytes >= need,
                     "tip_em_step: the slot-segmented mode needs %zu bytes of workspace (got %zu), see tip_em_workspace_bytes",
                     need, ws_bytes);
-        return launch_em_seg3(P, K, rows, n_rows, n_rows_r0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws), st);
+        return launch_em_seg3(P, K, rows, n_rows, n_rows_r0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws),
+                              (flags & TIP_EM_GATHER_L1) != 0, st);
     }
     if (uses_tuned(K, flags)) {
         const size_t need = em_tuned_workspace_bytes(P, K, seg_flag(flags));

@@ -88,7 +88,7 @@ int launch_em_tuned(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_ro
                     bool *handled, int phases = 7);
 size_t em_tuned_workspace_bytes(int P, int K, bool seg);
 int launch_em_seg3(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
-                   double *stats, double *ws, cudaStream_t st);
+                   double *stats, double *ws, bool gather_l1, cudaStream_t st);
 size_t em_seg3_workspace_bytes(int P, int K, int64_t n_rows);
 bool em_streamed_available(int K, bool with_ll, bool f32, bool seg);
 int launch_em_streamed(int P, int K, const void *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, double *stats,

@@ -57,7 +57,12 @@ struct S3 {
     static constexpr int LPI = (2 * U <= 32) ? 32 / (2 * U) : 0;       // whole links per gather instruction (0: flat mapping)
     static constexpr int ITERS = LPI ? (32 + LPI - 1) / LPI : 2 * U;
     static constexpr bool HOIST_Z = NB * NKG <= 12;                    // Z fragments of a run kept in registers
+    static constexpr int TP = (K + 15) / 16 * 16;                      // row stride of the gather copy of theta: rows start on
+                                                                       // 128-byte lines (one tag request and ceil(8K/32) sectors each)
 };
+
+constexpr int kS3Groups = 64;                 // chunk ranges / counters per launch
+constexpr int kS3CounterDoubles = 2 * kS3Groups * 16;   // two launches x groups x one 128-byte line, as doubles
 
 struct S3Args {
     int P;
@@ -66,12 +71,12 @@ struct S3Args {
     int tiles_per_order;
     int n_tiles_r0;          // rating-0 tiles of an order
     int slot0;               // first slot of this launch (0 or 1)
-    const double *theta;
+    const double *theta;     // [P][TP]: the 128-byte-aligned copy seg3_prep_kernel writes
     const double *Zg;        // [2][P][KK]            (pass A)
     double *sbuf;            // [tiles_per_order * 32] (written by pass A, read by pass BC)
     double *Mg;              // [3][2][P][KK]
-    unsigned *counter;       // chunk counter of this launch, zero on entry
-    int chunk;               // tiles per chunk
+    unsigned *counter;       // tile counter of this launch, zero on entry
+    int chunk;               // most tiles per draw
     int tune;                // bit 0: gather through L1 (cp.async.ca) instead of L2 only (.cg)
 };
 
@@ -88,19 +93,19 @@ __device__ __forceinline__ void cp_async_8_zfill(void *smem_dst, const void *gme
 }
 
 // theta rows of the 32 links of a tile -> stage[link][th_x | th_y].  K even: 16-byte copies, whole links per warp
-// instruction (a row is never split over two instructions, so its three sectors are requested once)
-template <int K>
-__device__ __forceinline__ void s3_gather(const double *__restrict__ theta, const int4 *ids_sm, double *stage, int lane,
-                                          bool ca)
+// instruction (a row is never split over two instructions, so its sectors are requested once).  CA: through L1
+// (cp.async.ca) - what hub-shaped links need, the few hub rows then stay in L1 instead of hammering a handful of L2
+// slices from every SM; .cg (L2 only) otherwise.  The gene ids are read first, then the copies are issued back to back.
+template <int K, bool CA>
+__device__ __forceinline__ void s3_gather(const double *__restrict__ theta, const int4 *ids_sm, double *stage, int lane)
 {
     using C = S3<K>;
     const int *idw = reinterpret_cast<const int *>(ids_sm);
-    auto copy = [&](int l, int slot, int k0) {
-        const int g = idw[l * 4 + 1 + slot];
+    auto copy = [&](int g, int l, int slot, int k0) {
         double *dst = stage + l * C::RS + slot * K + k0;
-        const double *src = theta + (int64_t)g * K + k0;
+        const double *src = theta + (int64_t)g * C::TP + k0;
         if (C::UNIT == 2) {
-            if (ca)
+            if (CA)
                 cp_async_16_ca(dst, src);
             else
                 cp_async_16(dst, src);
@@ -112,10 +117,16 @@ __device__ __forceinline__ void s3_gather(const double *__restrict__ theta, cons
         const int sub = lane / (2 * C::U), rem = lane - sub * (2 * C::U);
         const int slot = rem / C::U, k0 = (rem - slot * C::U) * C::UNIT;
         if (sub < C::LPI) {
+            int g[C::ITERS];
 #pragma unroll
             for (int it = 0; it < C::ITERS; ++it) {
                 const int l = it * C::LPI + sub;
-                if (32 % C::LPI == 0 || l < 32) copy(l, slot, k0);
+                g[it] = (32 % C::LPI == 0 || l < 32) ? idw[l * 4 + 1 + slot] : 0;
+            }
+#pragma unroll
+            for (int it = 0; it < C::ITERS; ++it) {
+                const int l = it * C::LPI + sub;
+                if (32 % C::LPI == 0 || l < 32) copy(g[it], l, slot, k0);
             }
         }
     } else {
@@ -124,13 +135,13 @@ __device__ __forceinline__ void s3_gather(const double *__restrict__ theta, cons
             const int u = it * 32 + lane;
             const int l = u / (2 * C::U), rem = u - l * (2 * C::U);
             const int slot = rem / C::U;
-            copy(l, slot, (rem - slot * C::U) * C::UNIT);
+            copy(idw[l * 4 + 1 + slot], l, slot, (rem - slot * C::U) * C::UNIT);
         }
     }
 }
 
 // NST stage buffers: the gathers of the next NST - 1 tiles are in flight while a tile is computed
-template <int K, bool FIRST, int NST>
+template <int K, bool FIRST, int NST, bool CA>
 __global__ void __launch_bounds__(32) seg3_pass_kernel(const S3Args a)
 {
     using C = S3<K>;
@@ -139,8 +150,6 @@ __global__ void __launch_bounds__(32) seg3_pass_kernel(const S3Args a)
     const int lane = threadIdx.x, li = lane & 3, ri = lane >> 2;
     auto stage_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * C::BUF_BYTES); };
     auto ids_of = [&](int b) { return reinterpret_cast<int4 *>(stage_of(b) + 32 * RS + 32); };
-    const bool ca = (a.tune & 1) != 0;
-
     // fragment coordinates of this lane: component i*8 + ri of an 8 x 8 block (rows/cols >= K read as zero)
     int xo[NB];
     bool xv[NB];
@@ -167,28 +176,46 @@ __global__ void __launch_bounds__(32) seg3_pass_kernel(const S3Args a)
                 acc[i][j][0] = acc[i][j][1] = 0.0;
             }
     };
-    auto mbase_of = [&](int tt) {
-        const int so = tt / a.tiles_per_order, tl = tt - so * a.tiles_per_order;
+    auto mbase_of = [&](int tt) {   // a launch walks one order (pass A) or two (pass B + C): no division needed
+        const int so = tt >= a.tiles_per_order ? 1 : 0, tl = tt - (so ? a.tiles_per_order : 0);
         return ((a.slot0 + so) * 2 + (tl >= a.n_tiles_r0 ? 1 : 0)) * a.P;
     };
 
-    // ---- tile sequence of this warp: chunks of consecutive tiles from an atomic counter, fetched one chunk ahead ----
+    // ---- tile sequence of this warp: chunks of consecutive tiles drawn from one atomic counter, guided self-scheduling:
+    // a draw asks for (remaining tiles) / (2 x warps), at most a.chunk and at least one tile - long chunks while there is
+    // plenty of work (few same-address atomics, which serialise in one L2 slice at about a nanosecond each, and few
+    // accumulator flushes), single tiles at the end (no tail).  Two draws are kept in flight per warp: the counter's
+    // round trip is a microsecond under load.
     int gen_t = 0, gen_end = 0;
     bool gen_done = false;
-    unsigned pend = 0;
-    if (lane == 0) pend = atomicAdd(a.counter, 1u);
+    unsigned pend = 0, pend_w = 0, pend2 = 0, pend2_w = 0;   // (first tile, tiles asked for) of the draws in flight; lane 0
+    auto guided = [&](unsigned pos) -> unsigned {
+        const unsigned rem = pos < (unsigned)a.n_tiles ? (unsigned)a.n_tiles - pos : 0u;
+        unsigned w = rem / (2u * gridDim.x);
+        w = w > (unsigned)a.chunk ? (unsigned)a.chunk : w;
+        return w < 1u ? 1u : w;
+    };
+    if (lane == 0) {
+        pend_w = pend2_w = guided(0u);
+        pend = atomicAdd(a.counter, pend_w);
+        pend2 = atomicAdd(a.counter, pend2_w);
+    }
     auto next_tile = [&]() -> int {
         if (gen_t < gen_end) return gen_t++;
         if (gen_done) return -1;
-        const unsigned c = __shfl_sync(0xffffffffu, pend, 0);
-        const long long t0 = (long long)c * a.chunk;
-        if (t0 >= a.n_tiles) {
+        const unsigned t0 = __shfl_sync(0xffffffffu, pend, 0), w = __shfl_sync(0xffffffffu, pend_w, 0);
+        if (t0 >= (unsigned)a.n_tiles) {
             gen_done = true;
             return -1;
         }
+        pend = pend2;
+        pend_w = pend2_w;
+        if (lane == 0) {
+            pend2_w = guided(t0 + w);
+            pend2 = atomicAdd(a.counter, pend2_w);
+        }
         gen_t = (int)t0;
-        gen_end = (t0 + a.chunk < a.n_tiles) ? (int)t0 + a.chunk : a.n_tiles;
-        if (lane == 0) pend = atomicAdd(a.counter, 1u);
+        gen_end = (t0 + w < (unsigned)a.n_tiles) ? (int)(t0 + w) : a.n_tiles;
         return gen_t++;
     };
     auto issue_gather = [&](int buf, const int4 &me) {
@@ -196,37 +223,55 @@ __global__ void __launch_bounds__(32) seg3_pass_kernel(const S3Args a)
         double *st = stage_of(buf);
         ids[lane] = me;
         __syncwarp();
-        s3_gather<K>(a.theta, ids, st, lane, ca);
-        if constexpr (!FIRST) cp_async_8_zfill(st + 32 * RS + lane, a.sbuf + (me.w >= 0 ? me.w : 0), me.w >= 0 ? 8 : 0);
+        if (!(a.tune & 2)) s3_gather<K, CA>(a.theta, ids, st, lane);   // (tune bit 1: timing experiment, wrong results)
+        if constexpr (!FIRST) if (!(a.tune & 8)) cp_async_8_zfill(st + 32 * RS + lane, a.sbuf + (me.w >= 0 ? me.w : 0), me.w >= 0 ? 8 : 0);
     };
 
-    int tq[NST];  // tq[0]: tile computed this iteration; tq[1 .. D-1]: gathers in flight; tq[D]: rows in me_pend
-    int4 me_pend = make_int4(0, 0, 0, 0);
+    // tq[0]: tile computed this iteration; tq[1 .. D-1]: gathers in flight; tq[D .. D+RQ-1]: rows held in registers
+    // (the rows come from HBM: RQ tiles of lookahead hide that latency)
+    constexpr int RQ = 2;
+    int tq[D + RQ];
+    int4 meq[RQ];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         tq[j] = next_tile();
         if (tq[j] >= 0) issue_gather(j, a.rows[(int64_t)tq[j] * 32 + lane]);
         cp_async_commit();
     }
-    tq[D] = next_tile();
-    if (tq[D] >= 0) me_pend = a.rows[(int64_t)tq[D] * 32 + lane];
+#pragma unroll
+    for (int j = 0; j < RQ; ++j) {
+        tq[D + j] = next_tile();
+        meq[j] = make_int4(0, 0, 0, 0);
+        if (tq[D + j] >= 0) meq[j] = a.rows[(int64_t)tq[D + j] * 32 + lane];
+    }
 
     int cb = 0;    // buffer of tq[0]
     int cur = -1;  // run the accumulators belong to (-1: none)
     int zcur = -1; // run whose Z fragments are in registers
-    double zf[C::HOIST_Z ? NB : 1][C::HOIST_Z ? NKG : 1];
-    (void)zcur; (void)zf;
+    int znext = -1; // run whose Z fragments were requested ahead (the first run of the next tile)
+    double zf[C::HOIST_Z ? NB : 1][C::HOIST_Z ? NKG : 1], zn[C::HOIST_Z ? NB : 1][C::HOIST_Z ? NKG : 1];
+    (void)zcur; (void)zf; (void)znext; (void)zn;
+    auto load_z = [&](double (&dst)[C::HOIST_Z ? NB : 1][C::HOIST_Z ? NKG : 1], int mrow_z) {
+        const double *Zr = a.Zg + (int64_t)mrow_z * KK;
+#pragma unroll
+        for (int j = 0; j < (C::HOIST_Z ? NB : 1); ++j)
+#pragma unroll
+            for (int kg = 0; kg < (C::HOIST_Z ? NKG : 1); ++kg)
+                dst[j][kg] = (xv[j] && 4 * kg + li < K) ? __ldg(Zr + xo[j] * K + 4 * kg + li) : 0.0;
+    };
 
     while (tq[0] >= 0) {
         // ---- A: gather of the tile D ahead; B: rows of the tile D + 1 ahead ----
         {
             int gb = cb + D;
             if (gb >= NST) gb -= NST;
-            if (tq[D] >= 0) issue_gather(gb, me_pend);
+            if (tq[D] >= 0) issue_gather(gb, meq[0]);
             cp_async_commit();
         }
         const int tn = next_tile();
-        if (tn >= 0) me_pend = a.rows[(int64_t)tn * 32 + lane];
+#pragma unroll
+        for (int j = 0; j + 1 < RQ; ++j) meq[j] = meq[j + 1];
+        if (tn >= 0) meq[RQ - 1] = a.rows[(int64_t)tn * 32 + lane];
         cp_async_wait<D>();
         __syncwarp();
 
@@ -255,12 +300,23 @@ __global__ void __launch_bounds__(32) seg3_pass_kernel(const S3Args a)
                 const double *Zr = a.Zg + (int64_t)mseg * KK;
                 if constexpr (C::HOIST_Z) {
                     if (mseg != zcur) {
+                        if (mseg == znext) {
 #pragma unroll
-                        for (int j = 0; j < NB; ++j)
+                            for (int j = 0; j < NB; ++j)
 #pragma unroll
-                            for (int kg = 0; kg < NKG; ++kg)
-                                zf[j][kg] = (xv[j] && 4 * kg + li < K) ? __ldg(Zr + xo[j] * K + 4 * kg + li) : 0.0;
+                                for (int kg = 0; kg < NKG; ++kg) zf[j][kg] = zn[j][kg];
+                        } else {
+                            load_z(zf, mseg);
+                        }
                         zcur = mseg;
+                    }
+                    if (l1 < 32) {
+                        // the next run of this tile: its Z fragments travel while this run is contracted
+                        const int mnext = __shfl_sync(0xffffffffu, mrow, l1);
+                        if (mnext != znext) {
+                            load_z(zn, mnext);
+                            znext = mnext;
+                        }
                     }
                 }
 #pragma unroll
@@ -303,6 +359,18 @@ __global__ void __launch_bounds__(32) seg3_pass_kernel(const S3Args a)
                 part += __shfl_xor_sync(0xffffffffu, part, 2);
                 if (li == rb) dsel = TIP_EPS + part;
             }
+            if constexpr (C::HOIST_Z && NST > 1) {
+                // Z fragments of the next tile's first run, requested now so that they land during the M phase below
+                if (tq[1] >= 0) {
+                    int nb_ = cb + 1;
+                    if (nb_ >= NST) nb_ -= NST;
+                    const int mnext = mbase_of(tq[1]) + ids_of(nb_)[0].x;
+                    if (mnext != zcur && mnext != znext) {
+                        load_z(zn, mnext);
+                        znext = mnext;
+                    }
+                }
+            }
             const int L = li * 8 + ri;
             // 1/d: fp32 reciprocal seed and three Newton steps (d lies in [1e-10, ~1]; last-ulp accuracy, see tip_em.cu)
             double rd = (double)__frcp_rn((float)dsel);
@@ -316,49 +384,70 @@ __global__ void __launch_bounds__(32) seg3_pass_kernel(const S3Args a)
         }
 
         // ---- M += (s th_x)^T . th_y over the runs of equal gene in this tile ----
-#pragma unroll 2
-        for (int ks = 0; ks < 8; ++ks) {
-            const unsigned nib = (bm >> (4 * ks)) & 15u;
-            const double *lrow = st + (4 * ks + li) * RS;
-            const double sv = ssm[4 * ks + li];
-            double av[NB], bv[NB];
+        if (a.tune & 4) {
+            // (tune bit 2: timing experiment, wrong results)
+        } else if (bm == 0u) {
+            // the whole tile continues the current run: eight unconditional k-steps
+#pragma unroll 4
+            for (int ks = 0; ks < 8; ++ks) {
+                const double *lrow = st + (4 * ks + li) * RS;
+                const double sv = ssm[4 * ks + li];
+                double av[NB], bv[NB];
 #pragma unroll
-            for (int i = 0; i < NB; ++i) {
-                av[i] = xv[i] ? lrow[xo[i]] * sv : 0.0;
-                bv[i] = xv[i] ? lrow[K + xo[i]] : 0.0;
-            }
-            if (nib == 0) {
+                for (int i = 0; i < NB; ++i) {
+                    av[i] = xv[i] ? lrow[xo[i]] * sv : 0.0;
+                    bv[i] = xv[i] ? lrow[K + xo[i]] : 0.0;
+                }
 #pragma unroll
                 for (int i = 0; i < NB; ++i)
 #pragma unroll
                     for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
-            } else {
-                // a run ends inside these four links: one masked product per segment
-                int j0 = 0;
-                while (j0 < 4) {
-                    if ((nib >> j0) & 1u) {
-                        flush(cur);
-                        cur = __shfl_sync(0xffffffffu, mrow, 4 * ks + j0);
-                    }
-                    const unsigned higher = nib >> (j0 + 1);
-                    const int len = higher ? __ffs(higher) : 4 - j0;
-                    const bool mine = li >= j0 && li < j0 + len;
+            }
+        } else {
+#pragma unroll 1
+            for (int ks = 0; ks < 8; ++ks) {
+                const unsigned nib = (bm >> (4 * ks)) & 15u;
+                const double *lrow = st + (4 * ks + li) * RS;
+                const double sv = ssm[4 * ks + li];
+                double av[NB], bv[NB];
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    av[i] = xv[i] ? lrow[xo[i]] * sv : 0.0;
+                    bv[i] = xv[i] ? lrow[K + xo[i]] : 0.0;
+                }
+                if (nib == 0) {
 #pragma unroll
                     for (int i = 0; i < NB; ++i)
 #pragma unroll
-                        for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], mine ? av[i] : 0.0, bv[j]);
-                    j0 += len;
+                        for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], av[i], bv[j]);
+                } else {
+                    // a run ends inside these four links: one masked product per segment
+                    int j0 = 0;
+                    while (j0 < 4) {
+                        if ((nib >> j0) & 1u) {
+                            flush(cur);
+                            cur = __shfl_sync(0xffffffffu, mrow, 4 * ks + j0);
+                        }
+                        const unsigned higher = nib >> (j0 + 1);
+                        const int len = higher ? __ffs(higher) : 4 - j0;
+                        const bool mine = li >= j0 && li < j0 + len;
+#pragma unroll
+                        for (int i = 0; i < NB; ++i)
+#pragma unroll
+                            for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], mine ? av[i] : 0.0, bv[j]);
+                        j0 += len;
+                    }
                 }
             }
         }
-        if (tq[1 % NST] != t + 1) {  // the warp's chunk ends here
+        if (tq[1] != t + 1) {  // the warp's chunk ends here
             flush(cur);
             cur = -1;
         }
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < D; ++j) tq[j] = tq[j + 1];
-        tq[D] = tn;
+        for (int j = 0; j + 1 < D + RQ; ++j) tq[j] = tq[j + 1];
+        tq[D + RQ - 1] = tn;
         if (++cb == NST) cb = 0;
     }
 }
@@ -366,31 +455,38 @@ __global__ void __launch_bounds__(32) seg3_pass_kernel(const S3Args a)
 // Z[r][g][b][c] = sum_a theta[g][a] p[a][b][c][r]  (one CTA per group of genes, p staged in shared memory), and the three
 // orientations of p the finish contracts with:
 //   PT[slot][r][k][e]:  slot 0: k = a, e = (b, c);  slot 1: k = b, e = (a, c);  slot 2: k = c, e = (a, b)
-constexpr int kPrepGenes = 8;
+constexpr int kPrepGenes = 16;
 __global__ void __launch_bounds__(256) seg3_prep_kernel(int P, int K, const double *__restrict__ theta,
                                                         const double *__restrict__ p, double *__restrict__ Zg,
-                                                        double *__restrict__ PT)
+                                                        double *__restrict__ PT, double *__restrict__ thpad, int TP)
 {
-    extern __shared__ double psm[];  // [2][K^3]  p[r][a][bc]   (only when it fits: K <= 20)
+    extern __shared__ double psm[];  // [2][K^3]  p[r][a][bc]  (K <= 20), then theta of this CTA's genes [kPrepGenes][K]
     const int KK = K * K, K3 = KK * K;
     const bool staged = K <= 20;
-    if (staged) {
-        for (int e = threadIdx.x; e < 2 * K3; e += blockDim.x) psm[(e & 1) * K3 + (e >> 1)] = __ldg(p + e);
-        __syncthreads();
-    }
+    double *tsm = psm + (staged ? 2 * K3 : 0);
     const int g0 = blockIdx.x * kPrepGenes;
-    const int n = 2 * kPrepGenes * KK;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        const int gi = e / (2 * KK), rem = e - gi * (2 * KK), r = rem / KK, bc = rem - r * KK;
-        const int g = g0 + gi;
-        if (g >= P) break;
-        const double *th = theta + (int64_t)g * K;
-        double z = 0.0;
-        if (staged)
-            for (int q = 0; q < K; ++q) z = fma(__ldg(th + q), psm[r * K3 + q * KK + bc], z);
-        else
-            for (int q = 0; q < K; ++q) z = fma(__ldg(th + q), __ldg(p + ((int64_t)q * KK + bc) * 2 + r), z);
-        Zg[((int64_t)r * P + g) * KK + bc] = z;
+    const int ng = (P - g0 < kPrepGenes) ? P - g0 : kPrepGenes;
+    if (staged)
+        for (int e = threadIdx.x; e < 2 * K3; e += blockDim.x) psm[(e & 1) * K3 + (e >> 1)] = __ldg(p + e);
+    for (int e = threadIdx.x; e < ng * K; e += blockDim.x) {
+        const double v = __ldg(theta + (int64_t)g0 * K + e);
+        tsm[e] = v;
+        const int gi = e / K;
+        thpad[(int64_t)(g0 + gi) * TP + (e - gi * K)] = v;   // the gather copy of theta: rows on 128-byte lines
+    }
+    __syncthreads();
+    // thread = (rating, b, c); the genes of the CTA in the inner loop
+    for (int rbc = threadIdx.x; rbc < 2 * KK; rbc += blockDim.x) {
+        const int r = rbc >= KK ? 1 : 0, bc = rbc - r * KK;
+        double *out = Zg + ((int64_t)r * P + g0) * KK + bc;
+        for (int gi = 0; gi < ng; ++gi) {
+            double z = 0.0;
+            if (staged)
+                for (int q = 0; q < K; ++q) z = fma(tsm[gi * K + q], psm[r * K3 + q * KK + bc], z);
+            else
+                for (int q = 0; q < K; ++q) z = fma(tsm[gi * K + q], __ldg(p + ((int64_t)q * KK + bc) * 2 + r), z);
+            out[(int64_t)gi * KK] = z;
+        }
     }
     // the transposed copies of p: spread over the CTAs
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < 6 * K3; f += gridDim.x * blockDim.x) {
@@ -426,19 +522,29 @@ __global__ void __launch_bounds__(kFin3Threads) seg3_finish_kernel(int P, const 
         double c[NB][2];
 #pragma unroll
         for (int i = 0; i < NB; ++i) c[i][0] = c[i][1] = 0.0;
+        constexpr int NE = (KK + 3) / 4;          // k-steps over the cells of M
+        constexpr int EB = NE < 32 ? NE : 32;     // loads in flight per batch
         for (int r = 0; r < 2; ++r) {
             const double *Mrow = Mg + ((int64_t)(slot * 2 + r) * P + (gv ? g : 0)) * KK;
             const double *Pr = PT + (int64_t)(slot * 2 + r) * K3;
-#pragma unroll 5
-            for (int e0 = 0; e0 < KK; e0 += 4) {
-                const int e = e0 + li;
-                const bool ev = e < KK;
-                const double av = (gv && ev) ? __ldg(Mrow + e) : 0.0;
+            for (int eb = 0; eb < NE; eb += EB) {
+                double av[EB];
 #pragma unroll
-                for (int i = 0; i < NB; ++i) {
-                    const int k = i * 8 + ri;
-                    const double bv = (k < K && ev) ? __ldg(Pr + k * KK + e) : 0.0;
-                    dmma884(c[i][0], c[i][1], av, bv);
+                for (int q = 0; q < EB; ++q) {
+                    const int e = (eb + q) * 4 + li;
+                    av[q] = (gv && e < KK) ? __ldg(Mrow + e) : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < EB; ++q) {
+                    const int e = (eb + q) * 4 + li;
+                    if (eb + q < NE) {
+#pragma unroll
+                        for (int i = 0; i < NB; ++i) {
+                            const int k = i * 8 + ri;
+                            const double bv = (k < K && e < KK) ? __ldg(Pr + k * KK + e) : 0.0;
+                            dmma884(c[i][0], c[i][1], av[q], bv);
+                        }
+                    }
                 }
             }
         }
@@ -484,10 +590,10 @@ __global__ void __launch_bounds__(kFin3Threads) seg3_finish_kernel(int P, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// workspace:  M[3][2][P][KK] | counters (32 doubles) | Z[2][P][ZK] | PT[3][2][K^3] | sbuf[n_rows]
+// workspace:  M[3][2][P][KK] | chunk counters | Z[2][P][ZK] | PT[3][2][K^3] | sbuf[n_rows]
 // ---------------------------------------------------------------------------------------------
 struct S3Layout {
-    size_t off_M, off_cnt, off_Z, off_PT, off_s, total;  // in doubles
+    size_t off_M, off_cnt, off_Z, off_PT, off_T, off_s, total;  // in doubles
 };
 static S3Layout s3_layout(int P, int K, int64_t n_rows)
 {
@@ -495,11 +601,12 @@ static S3Layout s3_layout(int P, int K, int64_t n_rows)
     S3Layout l;
     l.off_M = 0;
     l.off_cnt = 6 * (size_t)P * KK;
-    l.off_Z = l.off_cnt + 32;
+    l.off_Z = l.off_cnt + kS3CounterDoubles;
     l.off_PT = l.off_Z + 2 * (size_t)P * KK;
     l.off_PT = (l.off_PT + 1) / 2 * 2;
-    l.off_s = l.off_PT + 6 * KK * K;
-    l.off_s = (l.off_s + 1) / 2 * 2;
+    l.off_T = l.off_PT + 6 * KK * K;
+    l.off_T = (l.off_T + 15) / 16 * 16;                       // 128-byte aligned rows (the workspace base is)
+    l.off_s = l.off_T + (size_t)P * ((K + 15) / 16 * 16);
     l.total = l.off_s + (size_t)(n_rows < 32 ? 32 : n_rows);
     return l;
 }
@@ -516,48 +623,59 @@ static int s3_tune()
     return v;
 }
 
+// TIP_SEG3_SKIP (bit mask, timing experiments only - results are wrong): 1 memset, 2 prep, 4 pass A, 8 pass B+C, 16 finish
+static int s3_skip()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TIP_SEG3_SKIP");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 static int s3_chunk_tiles()
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("TIP_SEG3_CHUNK");
-        v = e ? atoi(e) : 2;
+        v = e ? atoi(e) : 8;
         if (v < 1) v = 1;
     }
     return v;
 }
 
-static int s3_stages()
+// stage buffers per warp: TIP_SEG3_STAGES_A / TIP_SEG3_STAGES_BC = 1 | 2 (1: no gather prefetch inside a warp, most warps per SM)
+static int s3_stages(bool first)
 {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("TIP_SEG3_STAGES");
-        v = e ? atoi(e) : 2;
-        if (v != 2 && v != 3) v = 2;
+    static int v[2] = {-1, -1};
+    if (v[first] < 0) {
+        const char *e = getenv(first ? "TIP_SEG3_STAGES_A" : "TIP_SEG3_STAGES_BC");
+        v[first] = e ? atoi(e) : 2;
+        if (v[first] != 1 && v[first] != 2) v[first] = 2;
     }
-    return v;
+    return v[first];
 }
 
-template <int K, bool FIRST, int NST>
+template <int K, bool FIRST, int NST, bool CA>
 static int s3_launch_pass_n(const S3Args &a, cudaStream_t st)
 {
     using C = S3<K>;
     constexpr size_t smem = C::BUF_BYTES * NST;
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
-        TIP_CHECK_CUDA(cudaFuncSetAttribute(seg3_pass_kernel<K, FIRST, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TIP_CHECK_CUDA(cudaFuncSetAttribute(seg3_pass_kernel<K, FIRST, NST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        TIP_CHECK_CUDA(cudaFuncSetAttribute(seg3_pass_kernel<K, FIRST, NST, CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TIP_CHECK_CUDA(cudaFuncSetAttribute(seg3_pass_kernel<K, FIRST, NST, CA>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                             cudaSharedmemCarveoutMaxShared));
         int nb = 0;
-        TIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seg3_pass_kernel<K, FIRST, NST>, 32, smem));
+        TIP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seg3_pass_kernel<K, FIRST, NST, CA>, 32, smem));
         TIP_REQUIRE(nb >= 1, "seg3_pass_kernel<%d> does not fit on an SM (smem %zu)", K, smem);
         blocks_per_sm = nb;
     }
-    const int64_t chunks = ((int64_t)a.n_tiles + a.chunk - 1) / a.chunk;
     const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
-    int grid = (int)(chunks < cap ? chunks : cap);
+    int grid = (int)(a.n_tiles < cap ? a.n_tiles : cap);
     if (grid < 1) grid = 1;
-    seg3_pass_kernel<K, FIRST, NST><<<grid, 32, smem, st>>>(a);
+    seg3_pass_kernel<K, FIRST, NST, CA><<<grid, 32, smem, st>>>(a);
     TIP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -565,27 +683,31 @@ static int s3_launch_pass_n(const S3Args &a, cudaStream_t st)
 template <int K, bool FIRST>
 static int s3_launch_pass(const S3Args &a, cudaStream_t st)
 {
-    if (s3_stages() == 3) return s3_launch_pass_n<K, FIRST, 3>(a, st);
-    return s3_launch_pass_n<K, FIRST, 2>(a, st);
+    const bool ca = (a.tune & 1) != 0;
+    if (s3_stages(FIRST) == 1) return ca ? s3_launch_pass_n<K, FIRST, 1, true>(a, st) : s3_launch_pass_n<K, FIRST, 1, false>(a, st);
+    return ca ? s3_launch_pass_n<K, FIRST, 2, true>(a, st) : s3_launch_pass_n<K, FIRST, 2, false>(a, st);
 }
 
 template <int K>
 static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
-                            double *stats, double *ws, cudaStream_t st)
+                            double *stats, double *ws, bool gather_l1, cudaStream_t st)
 {
     const S3Layout l = s3_layout(P, K, n_rows);
     const int KK = K * K;
     TIP_REQUIRE(n_rows / 32 < (1ll << 29), "tip_em_step: too many tiles in one shard for the slot-segmented kernels");
     // M and the chunk counters start from zero
-    TIP_CHECK_CUDA(cudaMemsetAsync(ws + l.off_M, 0, sizeof(double) * (l.off_cnt + 32), st));
-    {
-        const size_t smem = K <= 20 ? sizeof(double) * 2 * KK * K : 0;
+    const int skip = s3_skip();
+    if (!(skip & 1)) TIP_CHECK_CUDA(cudaMemsetAsync(ws + l.off_M, 0, sizeof(double) * (l.off_cnt + kS3CounterDoubles), st));
+    else TIP_CHECK_CUDA(cudaMemsetAsync(ws + l.off_cnt, 0, sizeof(double) * kS3CounterDoubles, st));
+    if (!(skip & 2)) {
+        const size_t smem = sizeof(double) * ((K <= 20 ? 2 * KK * K : 0) + kPrepGenes * K);
         static bool attr = false;
         if (!attr && smem > 48 * 1024) {
             TIP_CHECK_CUDA(cudaFuncSetAttribute(seg3_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
             attr = true;
         }
-        seg3_prep_kernel<<<(P + kPrepGenes - 1) / kPrepGenes, 256, smem, st>>>(P, K, theta, p, ws + l.off_Z, ws + l.off_PT);
+        seg3_prep_kernel<<<(P + kPrepGenes - 1) / kPrepGenes, 256, smem, st>>>(P, K, theta, p, ws + l.off_Z, ws + l.off_PT,
+                                                                              ws + l.off_T, S3<K>::TP);
         TIP_CHECK_CUDA(cudaGetLastError());
     }
     S3Args a;
@@ -593,24 +715,24 @@ static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_r
     a.rows = rows;
     a.tiles_per_order = (int)(n_rows / 32);
     a.n_tiles_r0 = (int)(n_rows_r0 / 32);
-    a.theta = theta;
+    a.theta = ws + l.off_T;
     a.Zg = ws + l.off_Z;
     a.sbuf = ws + l.off_s;
     a.Mg = ws + l.off_M;
     a.chunk = s3_chunk_tiles();
-    a.tune = s3_tune();
+    a.tune = s3_tune() | (gather_l1 ? 1 : 0);
     a.n_tiles = a.tiles_per_order;
     a.slot0 = 0;
     a.counter = reinterpret_cast<unsigned *>(ws + l.off_cnt);
-    int rc = s3_launch_pass<K, true>(a, st);
+    int rc = (skip & 4) ? 0 : s3_launch_pass<K, true>(a, st);
     if (rc) return rc;
     a.rows = rows + n_rows;
     a.n_tiles = 2 * a.tiles_per_order;
     a.slot0 = 1;
-    a.counter = reinterpret_cast<unsigned *>(ws + l.off_cnt) + 4;
-    rc = s3_launch_pass<K, false>(a, st);
+    a.counter = reinterpret_cast<unsigned *>(ws + l.off_cnt) + kS3Groups * 32;
+    rc = (skip & 8) ? 0 : s3_launch_pass<K, false>(a, st);
     if (rc) return rc;
-    {
+    if (!(skip & 16)) {
         constexpr int NBC = (K * K + 7) / 8;
         const int n_tasks = ((P + 7) / 8) * 3 + 2 * NBC * ((P + kFin3GeneChunk - 1) / kFin3GeneChunk);
         const int wpc = kFin3Threads / 32;
@@ -622,11 +744,11 @@ static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_r
 
 // rows: order a | order b | order c, n_rows rows each (tip_order_rows); stats zeroed by the caller
 int launch_em_seg3(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
-                   double *stats, double *ws, cudaStream_t st)
+                   double *stats, double *ws, bool gather_l1, cudaStream_t st)
 {
     switch (K) {
 #define TIP_S3_CASE(k) \
-    case k: return launch_em_seg3_k<k>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, st);
+    case k: return launch_em_seg3_k<k>(P, rows, n_rows, n_rows_r0, theta, p, stats, ws, gather_l1, st);
         TIP_S3_CASE(1) TIP_S3_CASE(2) TIP_S3_CASE(3) TIP_S3_CASE(4) TIP_S3_CASE(5) TIP_S3_CASE(6) TIP_S3_CASE(7) TIP_S3_CASE(8)
         TIP_S3_CASE(9) TIP_S3_CASE(10) TIP_S3_CASE(11) TIP_S3_CASE(12) TIP_S3_CASE(13) TIP_S3_CASE(14) TIP_S3_CASE(15)
         TIP_S3_CASE(16) TIP_S3_CASE(17) TIP_S3_CASE(18) TIP_S3_CASE(19) TIP_S3_CASE(20) TIP_S3_CASE(21) TIP_S3_CASE(22)

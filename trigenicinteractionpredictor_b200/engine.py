@@ -46,6 +46,7 @@ class EMEngine:
         self.P, self.K = int(P), int(K)
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.group = group
+        self._auto_flags = flags is None
         self.flags = default_flags(int(K)) if flags is None else int(flags)
         # group=None means "this process alone" (NOT torch.distributed's default group): link shards are opt-in
         self.world = _dist.world_size(group) if group is not None else 1
@@ -119,6 +120,13 @@ class EMEngine:
         self.train = self.pack(g1, g2, g3, n0, n1, want_deg=True)
         if self.flags & _cabi.TIP_EM_SLOT_SEGMENTED:
             self.order_rows(self.train)
+            if self._auto_flags:
+                # hub-shaped links (the 64 busiest genes hold more than a fifth of all link ends, as in a
+                # query-pair x array screen): gather theta through L1, see TIP_EM_GATHER_L1
+                deg = self.train.deg.to(torch.int64)
+                top = torch.topk(deg, min(64, deg.numel())).values.sum()
+                hubs = bool((top * 5 > deg.sum()).item()) and deg.numel() > 640
+                self.flags = (self.flags | _cabi.TIP_EM_GATHER_L1) if hubs else (self.flags & ~_cabi.TIP_EM_GATHER_L1)
         if global_deg is not None:
             self.train.deg = self._as_dev_i32(global_deg)
         elif self.world > 1:
