@@ -1,26 +1,34 @@
 #!/usr/bin/env python3
 """bench.py - EM link-updates/s of the MMSBM hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape kuzmin|uniform]
+                    [--skip cfg4,cfg3,fp32,k3,e2e,cpu,dist_check]
 
 A "step" is one EM iteration (Model.make_iteration, TIP.py:984-1043) over one rank's link shard.
-Workload at every N (weak scaling): BASELINE config 2 per GPU - 6,000 genes, K=10, the fold-1
-training split of 1M triplets = 800,000 links per rank; with N>1 the links are sharded over ranks
-(N x 800,000 links in total) and every iteration carries one NCCL allreduce of the statistics.
-`--workload cfg4` runs BASELINE config 4 instead (1e8 links in total, strong scaling).
+Headline workload at every N (weak scaling): BASELINE config 2 per GPU - Kuzmin-2018 trigenic shape, 6,000 genes,
+K=10, the fold-1 training split of 1M triplets = 800,000 links per rank; with N>1 the links are sharded over the
+ranks (N x 800,000 links in total) and every iteration sums the statistics across ranks (NVLink peer memory fused
+into the M-step kernel, or NCCL).  On the same line, each with its own key: the uniform-triple shape of the same
+size, BASELINE config 4 (1e8 links in total, STRONG scaling over the N ranks, `cfg4_strong`) and config 3 (50
+random-restart samples spread over the N ranks, no communication, `cfg3_samples`).
 
-Prints ONE JSON line on rank 0.  `value` = link-updates/s with inputs resident in HBM; `e2e` = the
-same through the host-buffer C-ABI call (H2D of rows/theta/p and D2H of theta/p inside the timed
-region); `roofline` is against the fp64 FMA peak MEASURED in this run (the kernel is DFMA bound,
-6*K^3 flops per link-update); `cpu_baseline` is the CPython oracle port on this box's cores.
+Prints ONE JSON line on rank 0.  `value` = link-updates/s with inputs resident in HBM; `e2e` = the same through the
+host-buffer C-ABI call (H2D of rows/theta/p and D2H of theta/p inside the timed region); `roofline` describes the
+dominant kernel (the slot-segmented pass kernel) by SURVEY section 8d's accounting and names what binds it;
+`cpu_baseline` is the reference's own Model.make_iteration (oracle/_ref, kind "reference") - or the oracle's
+literal-loop port when the reference script did not travel (kind "port") - on this box's host cores.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
+import ctypes
+import io
 import json
 import os
 import statistics
 import sys
+import tempfile
 import threading
 import time
 
@@ -29,7 +37,9 @@ sys.path.insert(0, ROOT)
 
 P_GENES, K_GROUPS = 6000, 10
 L_PER_GPU = 800_000
+T_TEST = 200_000
 CFG4_LINKS = 100_000_000
+CFG3_SAMPLES = 50
 METRIC = "EM link-updates/sec at K=10"
 UNIT = "link-updates/s"
 
@@ -89,45 +99,95 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- CPU legs
-def _cpu_worker(args):
-    """One core: literal-loop oracle EM step (the CPython reference restated) on its own link sample."""
-    seed, n_links, P, K = args
+# One worker process per host core (the stand-in for the reference's `parallel --jobs N` over samples, run.sh:36-45;
+# GNU parallel and pypy3 are not in the image).  Each worker holds ONE model on its own sample of links and a "step" is
+# one EM iteration of every worker's model at the same time.
+_W = {}
+
+
+def _cpu_init(kind, seed0, n_links, P, K):
+    """Pool initializer: build this worker's model.  kind "reference": the unmodified reference script from
+    oracle/_ref (Model.get_traintest on files written here, initialize_parameters, then make_iteration per step);
+    kind "port": the oracle's literal-loop restatement of the same loops."""
+    import random
     import numpy as np
-    from oracle import mmsbm_oracle as orc
+    seed = seed0 + os.getpid() % 9973
     rng = np.random.default_rng(seed)
+    # a cfg2-shaped sample: ids drawn from P genes; every gene of the sample has a training link
     ids = rng.integers(0, P, size=(n_links, 3))
-    ids[:, 0] = np.arange(n_links) % P
+    ids[:, 1] = (ids[:, 0] + 1 + rng.integers(0, P - 1, n_links)) % P
+    ids[:, 2] = (ids[:, 1] + 1 + rng.integers(0, P - 2, n_links)) % P
+    ids[ids[:, 2] == ids[:, 0], 2] = (ids[ids[:, 2] == ids[:, 0], 2] + 1) % P
     lab = (rng.random(n_links) < 0.1).astype(int)
-    cnt = np.stack([1 - lab, lab], axis=1)
-    theta = rng.dirichlet(np.ones(K), size=P).tolist()
-    pr = rng.random((K, K, K, 2))
-    pr = (pr / pr.sum(axis=3, keepdims=True)).tolist()
-    deg_ok = np.bincount(ids.ravel(), minlength=P)
-    # genes without a link in this sample would raise ZeroDivisionError; restrict theta to covered genes
-    remap = -np.ones(P, dtype=int)
-    used = np.nonzero(deg_ok)[0]
-    remap[used] = np.arange(len(used))
-    ids = remap[ids]
-    theta = [theta[g] for g in used]
+    _W["kind"], _W["n"] = kind, n_links
+    if kind == "reference":
+        from oracle import fetch_ref
+        mod = fetch_ref.load_reference_module()
+        tmp = tempfile.mkdtemp(prefix="tipref_")
+        seen = {}
+        with open(os.path.join(tmp, "train.dat"), "w") as fh:
+            for (a, b, c), r in zip(ids.tolist(), lab.tolist()):
+                key = tuple(sorted((a, b, c)))
+                if len(set(key)) < 3 or key in seen:
+                    continue
+                seen[key] = 1
+                fh.write("G%05d_G%05d_G%05d\t%d\n" % (key[0], key[1], key[2], r))
+        with open(os.path.join(tmp, "test.dat"), "w") as fh:
+            a, b, c = next(iter(seen))                 # a test link over genes that all have a training link (TIP.py:1018)
+            fh.write("G%05d_G%05d_G%05d\t0\n" % (a, b, c))
+        m = mod.Model()
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.get_traintest(os.path.join(tmp, "train.dat"), os.path.join(tmp, "test.dat"))
+        random.seed(seed)
+        m.initialize_parameters(K)
+        _W["model"], _W["n"] = m, len(m.links)
+    else:
+        from oracle import mmsbm_oracle as orc
+        cnt = np.stack([1 - lab, lab], axis=1)
+        used = np.unique(ids)
+        remap = -np.ones(P, dtype=int)
+        remap[used] = np.arange(len(used))
+        theta = rng.dirichlet(np.ones(K), size=len(used)).tolist()
+        pr = rng.random((K, K, K, 2))
+        pr = (pr / pr.sum(axis=3, keepdims=True)).tolist()
+        _W["orc"], _W["theta"], _W["pr"] = orc, theta, pr
+        _W["ids"], _W["cnt"] = remap[ids].tolist(), cnt.tolist()
+
+
+def _cpu_step(_):
     t0 = time.perf_counter()
-    orc.em_step_loops(theta, pr, ids.tolist(), cnt.tolist())
-    return time.perf_counter() - t0
+    if _W["kind"] == "reference":
+        _W["model"].make_iteration()
+    else:
+        _W["theta"], _W["pr"] = _W["orc"].em_step_loops(_W["theta"], _W["pr"], _W["ids"], _W["cnt"])[:2]
+    return _W["n"], time.perf_counter() - t0
 
 
-def cpu_port_rate(links_per_core: int, P: int, K: int, steps: int = 1):
-    """CPython loops on every host core, one independent sample per core (stand-in for the
-    reference's `parallel --jobs N` over samples).  Returns (link-updates/s, cores, seconds)."""
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    ctx = mp.get_context("spawn")
-    total_t, total_links = 0.0, 0
-    with ctx.Pool(cores) as pool:
-        for s in range(steps):
-            t0 = time.perf_counter()
-            pool.map(_cpu_worker, [(1000 + s * cores + c, links_per_core, P, K) for c in range(cores)])
-            total_t += time.perf_counter() - t0
-            total_links += links_per_core * cores
-    return total_links / total_t, cores, total_t
+class CpuArm:
+    """All host cores, one model per core.  step() = one EM iteration on every core; returns (links, seconds)."""
+
+    def __init__(self, links_per_core, P, K, kind=None):
+        import multiprocessing as mp
+        from oracle import fetch_ref
+        if kind is None:
+            kind = "reference" if fetch_ref.load_reference_module() is not None else "port"
+        self.kind, self.cores, self.links_per_core = kind, os.cpu_count() or 1, links_per_core
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_init, initargs=(kind, 1000, links_per_core, P, K))
+
+    def step(self):
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_step, range(self.cores), chunksize=1)
+        return sum(n for n, _ in res), time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def describe(self, secs):
+        what = ("the unmodified reference TrigenicInteractionPredictor.py (oracle/_ref), Model.make_iteration" if self.kind == "reference"
+                else "CPython literal-loop oracle port of Model.make_iteration (oracle/_ref absent)")
+        return "%d cores x ~%d links per step, one model per core: %s, K=%d, P=%d (%.1f s); cost is linear in links" % (
+            self.cores, self.links_per_core, what, K_GROUPS, P_GENES, secs)
 
 
 def c_port_rate(n_links: int, P: int, K: int):
@@ -149,31 +209,36 @@ def c_port_rate(n_links: int, P: int, K: int):
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's CPU implementation of the path.  The reference is pure
-    Python and cannot travel to the GPU box, so the oracle's literal-loop port is timed (kind "port")."""
+    """`--impl reference`: the reference's own CPU implementation of the path on every host core - the unmodified
+    TIP.py from oracle/_ref when it travelled with the tree (kind "reference"), else the oracle's port (kind "port").
+    Same warm-up and step counts as asked; the links per core are sized so that the whole run stays within minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    links_per_core = 1500
-    cpu_port_rate(100, P_GENES, K_GROUPS)                     # warm-up: imports, pool start
-    t_all, rates, cores = [], [], 1
-    budget_s, t_begin = 150.0, time.perf_counter()
-    for _ in range(max(1, args.steps)):
-        rate, cores, secs = cpu_port_rate(links_per_core, P_GENES, K_GROUPS)
-        rates.append(rate)
-        t_all.append(secs)
-        if time.perf_counter() - t_begin > budget_s:
-            break                                             # bounded: the whole run stays within minutes
-    steps = len(rates)
-    value = sum(rates) / steps
-    sample = "%d cores x %d links per step, CPython literal-loop oracle port, K=%d, P=%d" % (
-        cores, links_per_core, K_GROUPS, P_GENES)
+    warm, steps = max(args.warmup, 0), max(args.steps, 1)
+    probe = CpuArm(100, P_GENES, K_GROUPS)
+    probe.step()
+    n, secs = probe.step()
+    probe.close()
+    per_core_rate = n / probe.cores / secs
+    budget_s = 150.0
+    links_per_core = int(max(60, min(1500, budget_s * per_core_rate / (warm + steps))))
+    arm = CpuArm(links_per_core, P_GENES, K_GROUPS, kind=probe.kind)
+    for _ in range(warm):
+        arm.step()
+    links, t_all = 0, 0.0
+    for _ in range(steps):
+        n, secs = arm.step()
+        links += n
+        t_all += secs
+    arm.close()
+    value = links / t_all
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": 1, "ms_per_step": 1e3 * sum(t_all) / steps, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_all / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg2 shape (6000 genes, K=10): bounded sample of %d links per step" % (links_per_core * cores)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        "config": {"workload": "cfg2 shape (6000 genes, K=10): bounded sample of %d links per step" % (links // steps)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.describe(t_all),
                          "pypy3": "unavailable in image"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -183,6 +248,33 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+def _links(synth, shape, P, L, seed, dev):
+    import torch
+    if shape == "kuzmin":
+        g1, g2, g3, lab = synth.kuzmin_links_soa(P, L, seed=seed, device=dev)
+    else:
+        g1, g2, g3, lab = synth.planted_links_soa(P, L, seed=seed, device=dev)
+    g1[:P] = torch.arange(P, dtype=torch.int32, device=dev)            # every gene has a training link
+    return g1, g2, g3, 1 - lab, lab
+
+
+def _timed_replays(torch, eng, steps, warmup, flush_l2, dev):
+    """ms of each of `steps` graph replays (CUDA events on the launching stream), L2 flushed before every one."""
+    for _ in range(warmup):
+        flush_l2()
+        eng.graph_step()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    torch.cuda.synchronize(dev)
+    for i in range(steps):
+        flush_l2()
+        ev0[i].record()
+        eng.graph_step()
+        ev1[i].record()
+    torch.cuda.synchronize(dev)
+    return [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -197,174 +289,202 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     lib = _cabi.load()
     P, K = P_GENES, K_GROUPS
-    if args.workload == "cfg4":
-        lo, hi = tdist.shard_bounds(CFG4_LINKS, rank, world)
-        L_local, L_total, scaling = hi - lo, CFG4_LINKS, "strong"
-        workload = "cfg4: 6000 genes x 1e8 triplets, K=10, link-sharded over %d GPU(s)" % world
-    else:
-        L_local, L_total, scaling = L_PER_GPU, L_PER_GPU * world, "weak"
-        workload = ("cfg2: 6000 genes x 1M triplets, K=10, fold-1 train split = 800,000 links per GPU"
-                    + ("" if world == 1 else "; %d link shards, statistics summed across ranks every iteration (%s)" % (
-                        world, "NVLink peer memory, fused into the M-step kernel" if args.exchange == "peer" else "NCCL allreduce")))
+    skip = set(x for x in args.skip.split(",") if x)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    L_local, L_total = L_PER_GPU, L_PER_GPU * world
+    shape_txt = {"kuzmin": "Kuzmin-2018 trigenic shape ((query pair) x array gene, 77 hub genes of degree ~20,000)",
+                 "uniform": "uniform random triples"}
+    workload = ("cfg2: 6000 genes x 1M triplets, K=10, %s, fold-1 train split = 800,000 links per GPU" % shape_txt[args.shape]
+                + ("" if world == 1 else "; %d link shards, statistics summed across ranks every iteration (%s)" % (
+                    world, "NVLink peer memory, fused into the M-step kernel" if args.exchange == "peer" else "NCCL allreduce")))
 
     group = torch.distributed.group.WORLD if world > 1 else None
-    eng = EMEngine(P, K, device=dev, group=group, exchange=args.exchange)
-    g1, g2, g3, lab = synth.planted_links_soa(P, L_local, seed=100 + rank, device=dev)
-    g1[:P] = torch.arange(P, dtype=torch.int32, device=dev)            # every gene has a training link
-    eng.set_train_links(g1, g2, g3, 1 - lab, lab)
-    del g1, g2, g3, lab
     rng = np.random.default_rng(0)
     theta0 = rng.dirichlet(np.ones(K), size=P)
     pr0 = rng.random((K, K, K, 2))
     pr0 /= pr0.sum(axis=3, keepdims=True)
-    eng.set_params(theta0, pr0)
-
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)    # 4x the 126 MB L2
 
     def flush_l2():
         flush.zero_()
 
-    # one iteration captured in a CUDA graph (E-step, statistics exchange, M-step); two graphs when the
-    # statistics are double-buffered for the peer-memory exchange
-    eng.capture_graphs()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ------------------------------------------------------------------ headline: cfg2 per GPU, default E-step
+    eng = EMEngine(P, K, device=dev, group=group, exchange=args.exchange)
+    eng.set_train_links(*_links(synth, args.shape, P, L_local, 100 + rank, dev))
+    eng.set_params(theta0, pr0)
+    eng.capture_graphs()               # one iteration (E-step, statistics exchange, M-step) per CUDA graph
     launches_per_step = eng._graph_launches
     eng.set_params(theta0, pr0)
-
-    class _Replay:
-        @staticmethod
-        def replay():
-            eng.graph_step()
-    graph = _Replay
-
     sampler = ClockSampler(local)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         flush_l2()
-        graph.replay()
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        eng.graph_step()
     tdist.barrier(group)
     torch.cuda.synchronize(dev)
-    for i in range(args.steps):
-        flush_l2()
-        ev0[i].record()
-        graph.replay()
-        ev1[i].record()
-    torch.cuda.synchronize(dev)
+    ms = _timed_replays(torch, eng, steps, 0, flush_l2, dev)
     tdist.barrier(group)
-    local_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
-    total_ms = tdist.max_over_ranks(local_ms, device=dev, group=group)
-    ms_per_step = total_ms / args.steps
+    total_ms = tdist.max_over_ranks(sum(ms), device=dev, group=group)
+    ms_per_step = total_ms / steps
     value = L_total / (ms_per_step * 1e-3)
 
     # back-to-back replays, rows resident in L2 (how a real training run behaves) - informational
     torch.cuda.synchronize(dev)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(args.steps):
-        graph.replay()
+    for _ in range(steps):
+        eng.graph_step()
     b.record()
     torch.cuda.synchronize(dev)
-    warm_ms = tdist.max_over_ranks(a.elapsed_time(b) / args.steps, device=dev, group=group)
-
-    # dominant kernel alone (E-step): CUDA events on the launching stream, L2 flushed before each
-    k_ms = []
-    for _ in range(max(5, min(args.steps, 20))):
-        flush_l2()
-        a.record()
-        eng.em_step()
-        b.record()
-        torch.cuda.synchronize(dev)
-        k_ms.append(a.elapsed_time(b))
+    warm_ms = tdist.max_over_ranks(a.elapsed_time(b) / steps, device=dev, group=group)
     clocks = sampler.stop()
-    kernel_ms = statistics.mean(k_ms)
+
+    # the kernels of one E-step, each timed with CUDA events on the launching stream (un-graphed, L2 flushed)
+    seg3 = bool(eng.flags & _cabi.TIP_EM_SLOT_SEGMENTED)
+    stage_ms = None
+    if seg3:
+        lib.tip_seg3_timing(1)
+        acc = []
+        buf = (ctypes.c_float * 5)()
+        for _ in range(max(5, min(steps, 20))):
+            flush_l2()
+            eng.em_step()
+            _cabi.check(lib.tip_seg3_last_timing(buf), "tip_seg3_last_timing")
+            acc.append(list(buf))
+        lib.tip_seg3_timing(0)
+        stage_ms = [statistics.mean(x[i] for x in acc) for i in range(5)]
     n_rows = eng.train.n_rows
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "P": P, "K": K, "links_per_gpu": L_local, "links_total": L_total,
+        "config": {"workload": workload, "P": P, "K": K, "links_per_gpu": L_local, "links_total": L_total, "shape": args.shape,
+                   "estep": "slot-segmented (TIP_EM_SLOT_SEGMENTED%s)" % (" | TIP_EM_GATHER_L1" if eng.flags & _cabi.TIP_EM_GATHER_L1 else "")
+                   if seg3 else "flags %d" % eng.flags,
                    "l2": "flushed (512 MB memset) before every timed step", "cuda_graph": True},
         "value_l2_warm": L_total / (warm_ms * 1e-3),
-        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches": launches_per_step * steps,
         "clocks": clocks,
     }
 
+    # replicas of theta / p must be bit-identical on every rank after the timed iterations
+    if world > 1:
+        chk = torch.stack([eng.theta.view(torch.int64).sum(), eng.p.view(torch.int64).sum()])
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        torch.distributed.all_gather(allc, chk, group=group)
+        line["replicas_bit_identical"] = bool(all(torch.equal(c, allc[0]) for c in allc))
+        eng._check_peer()
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
     if rank == 0:
-        # ---- roofline of the E-step kernel against the fp64 FMA peak measured now ----
-        peak64, peak32 = _measure_peak(lib, 0), _measure_peak(lib, 1)
-        flops = 6.0 * K ** 3 * L_local
-        achieved = flops / (kernel_ms * 1e-3) / 1e12
+        peak_dfma, peak_dmma, peak32 = _measure_peak(lib, 0), _measure_peak(lib, 2), _measure_peak(lib, 1)
+        gath = ctypes.c_double(0.0)
+        _cabi.check(lib.tip_measure_l2_gather(P, 8 * K, ctypes.byref(gath)), "tip_measure_l2_gather")
         peaks = _read_peaks()
-        prof = _read_profile()
-        line["roofline"] = {
-            "bound": "fp64_fma", "achieved": achieved, "peak": peak64, "unit": "TFLOP/s", "frac": achieved / peak64,
-            "traffic": prof.get("traffic_bytes"), "kernel": "tip_em_step: em_fused_kernel<10> (88 % of the step) + em_finalize_kernel<10>",
-            "kernel_ms": kernel_ms, "flops_per_link_update": 6 * K ** 3,
-            "peak_source": "tip_measure_fma_peak(DFMA) measured in this run (no fp64 figure in MEASURED_PEAKS.json)",
-            "ncu_fp64_pipe_pct": prof.get("fp64_pipe_pct"), "ncu_source": prof.get("source"),
-            "fp32_fma_peak": peak32,
-            "hbm": {"algorithmic_bytes": 16 * n_rows, "achieved_gbs": 16 * n_rows / (kernel_ms * 1e-3) / 1e9,
-                    "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json" if peaks else "absent"},
-        }
+        if seg3:
+            k_ms = stage_ms[2] + stage_ms[3]
+            flops = 6.0 * K ** 3 * L_local
+            achieved = flops / (k_ms * 1e-3) / 1e12
+            sect = (8 * K + 31) // 32 * 32
+            l2_bytes = L_local * (6 * sect + 3 * 16 + 3 * 8)       # six theta rows, three row reads, s written once + read twice
+            prof = _read_profile("r2_seg3_pass_metrics.json")
+            line["roofline"] = {
+                "bound": "fp64_fma", "achieved": achieved, "peak": peak_dmma, "unit": "TFLOP/s", "frac": achieved / peak_dmma,
+                "traffic": prof.get("traffic_bytes"), "traffic_source": prof.get("source", "no ncu capture in the tree"),
+                "kernel": "seg3_pass_kernel<10,...>: pass A + pass B/C launches (one E-step walks every link in three orders)",
+                "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step if world == 1 else None,
+                "estep_stage_ms": dict(zip(["memset", "prep", "pass_a", "pass_bc", "finish"], stage_ms)),
+                "flops_per_link_update": 6 * K ** 3,
+                "accounting": "SURVEY 8d: achieved = 6 K^3 flop x links / duration of the kernel.  The kernel EXECUTES 8 K^2 flop "
+                              "per link on the fp64 tensor path (DMMA) plus 4 K^3 per (gene, rating) in the prep / finish kernels: the "
+                              "factorisation removes the K^3-per-link contraction, so the algorithmic rate is not a pipe utilisation",
+                "peak_source": "tip_measure_fma_peak(kind 2: mma.sync m8n8k4 f64) measured in this run; DFMA chains read %.2f" % peak_dfma,
+                "executed_tflops": 8.0 * K * K * L_local / (k_ms * 1e-3) / 1e12,
+                "binding": {"resource": "L2 gather latency (six theta rows per link from L2; warps wait on the gathers)",
+                            "l2_bytes_per_link": l2_bytes / L_local, "achieved_gbs": l2_bytes / (k_ms * 1e-3) / 1e9,
+                            "peak_gbs": gath.value, "frac": l2_bytes / (k_ms * 1e-3) / 1e9 / gath.value,
+                            "peak_source": "tip_measure_l2_gather: random %d-byte rows of a %d-row table, 16-byte L2-only loads, measured in this run" % (8 * K, P)},
+                "ncu": {k: prof.get(k) for k in ("lts_t_bytes", "issue_active_pct", "fp64_pipe_pct", "stall_mix") if k in prof},
+                "fp32_fma_peak": peak32,
+                "hbm": {"algorithmic_bytes": 16 * n_rows, "achieved_gbs": 16 * n_rows * 3 / (k_ms * 1e-3) / 1e9,
+                        "peak_gbs": peaks.get("hbm_gbs"), "peak_source": "MEASURED_PEAKS.json" if peaks else "absent",
+                        "note": "three orders of the rows are streamed per E-step: 48 B per link"},
+            }
+        else:
+            line["roofline"] = None
     else:
         line["roofline"] = None
+        peak_dfma = peak32 = None
 
-    # ---- fp32-compute / fp64-accumulate mode (north_star's 1e-5 mode), same workload, informational ----
+    # ------------------------------------------------------------------ the other shape at the same size
+    other = "uniform" if args.shape == "kuzmin" else "kuzmin"
     if world == 1:
-        eng32 = EMEngine(P, K, device=dev, flags=_cabi.TIP_EM_FP32_COMPUTE)
-        eng32.train, eng32.em_ws, eng32.em_ws_bytes = eng.train, eng.em_ws, eng.em_ws_bytes
-        eng32.set_params(theta0, pr0)
-        eng32.capture_graphs()
-        for _ in range(3):
-            flush_l2()
-            eng32.graph_step()
-        t32 = 0.0
-        for _ in range(args.steps):
-            flush_l2()
-            a.record()
-            eng32.graph_step()
-            b.record()
-            torch.cuda.synchronize(dev)
-            t32 += a.elapsed_time(b)
-        line["value_fp32_compute"] = L_total / (t32 / args.steps * 1e-3)
-        line["fp32_compute_roofline_frac"] = (6.0 * K ** 3 * L_local / (t32 / args.steps * 1e-3) / 1e12) / peak32 if rank == 0 else None
-        del eng32
-        # ---- gene-segmented mode (TIP_EM_GENE_SEGMENTED): 2K^2 instead of 2K^3 FMA per link; not FMA bound ----
-        engs = EMEngine(P, K, device=dev, flags=_cabi.TIP_EM_GENE_SEGMENTED)
-        engs.set_train_links(*_links_again(synth, P, L_local, rank, dev))
-        engs.set_params(theta0, pr0)
-        engs.capture_graphs()
-        for _ in range(3):
-            flush_l2()
-            engs.graph_step()
-        ts = 0.0
-        for _ in range(args.steps):
-            flush_l2()
-            a.record()
-            engs.graph_step()
-            b.record()
-            torch.cuda.synchronize(dev)
-            ts += a.elapsed_time(b)
-        line["value_gene_segmented"] = L_total / (ts / args.steps * 1e-3)
-        line["gene_segmented_note"] = ("same statistics to rounding with 2K^2+K^2 FMA per link (+2K^3 per gene and rating); "
-                                       "bound by the theta gather and the fp64 reductions, so it is reported beside, not as, "
-                                       "the FMA-roofline kernel")
-        del engs
+        eo = EMEngine(P, K, device=dev)
+        eo.set_train_links(*_links(synth, other, P, L_local, 100 + rank, dev))
+        eo.set_params(theta0, pr0)
+        eo.capture_graphs()
+        eo.set_params(theta0, pr0)
+        mo = _timed_replays(torch, eo, steps, 3, flush_l2, dev)
+        line["value_" + other] = L_total / (statistics.mean(mo) * 1e-3)
+        line["value_" + args.shape] = value
+        line["shape_ratio_kuzmin_over_uniform"] = (line["value_kuzmin"] / line["value_uniform"])
+        del eo
 
-    # ---- end to end through host buffers ----
-    e2e = _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist)
-    line["e2e"] = e2e
+    # ------------------------------------------------------------------ the K^3-per-link kernel and the 1e-5 mode
+    if world == 1 and "k3" not in skip:
+        ek = EMEngine(P, K, device=dev, flags=_cabi.TIP_EM_DEFAULT)
+        ek.set_train_links(*_links(synth, "uniform", P, L_local, 100 + rank, dev))
+        ek.set_params(theta0, pr0)
+        ek.capture_graphs()
+        ek.set_params(theta0, pr0)
+        mk = statistics.mean(_timed_replays(torch, ek, steps, 3, flush_l2, dev))
+        line["k3_per_link_kernel"] = {
+            "value": L_total / (mk * 1e-3), "ms_per_step": mk, "shape": "uniform",
+            "roofline_frac_dfma": (6.0 * K ** 3 * L_local / (mk * 1e-3) / 1e12) / peak_dfma,
+            "note": "em_fused_kernel<10>: 2 K^3 DFMA per link in registers (TIP_EM_DEFAULT); executes what it is charged for"}
+        if "fp32" not in skip:
+            e32 = EMEngine(P, K, device=dev, flags=_cabi.TIP_EM_FP32_COMPUTE)
+            e32.train, e32.em_ws, e32.em_ws_bytes = ek.train, ek.em_ws, ek.em_ws_bytes
+            e32.set_params(theta0, pr0)
+            e32.capture_graphs()
+            e32.set_params(theta0, pr0)
+            m32 = statistics.mean(_timed_replays(torch, e32, steps, 3, flush_l2, dev))
+            line["value_fp32_compute"] = L_total / (m32 * 1e-3)
+            line["fp32_compute_roofline_frac"] = (6.0 * K ** 3 * L_local / (m32 * 1e-3) / 1e12) / peak32
+            del e32
+        del ek
+
+    # ------------------------------------------------------------------ end to end through host buffers
+    if "e2e" not in skip:
+        line["e2e"] = _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist)
+    del eng
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ link-shard correctness gate (N > 1)
+    if world > 1 and "dist_check" not in skip:
+        line["dist_check"] = _dist_check(rank, world, dev, group, args.exchange, tdist)
+
+    # ------------------------------------------------------------------ cfg4: 1e8 links, strong scaling
+    if "cfg4" not in skip:
+        line["cfg4_strong"] = _cfg4(rank, world, dev, group, args, theta0, pr0, flush_l2, synth, tdist)
+    # ------------------------------------------------------------------ cfg3: 50 restarts, sample-parallel
+    if "cfg3" not in skip:
+        line["cfg3_samples"] = _cfg3(rank, world, dev, group, synth, tdist)
 
     if rank == 0:
-        if world == 1 and not args.no_cpu:
-            rate, cores, secs = cpu_port_rate(1500, P, K)
+        if world == 1 and "cpu" not in skip and not args.no_cpu:
+            arm = CpuArm(1500, P, K)
+            links, secs = 0, 0.0
+            for _ in range(3):
+                n, s = arm.step()
+                links += n
+                secs += s
+            arm.close()
             crate, ccores = c_port_rate(40000, P, K)
             line["cpu_baseline"] = {
-                "value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": "%d cores x 1500 links, one CPython literal-loop EM step each (%.1f s); "
-                          "cost is linear in links" % (cores, secs),
+                "value": links / secs, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.describe(secs),
                 "c_port_openmp_value": crate, "c_port_cores": ccores, "pypy3": "unavailable in image"}
         else:
             line["cpu_baseline"] = None
@@ -380,15 +500,123 @@ def run_ours(args):
     return 0
 
 
-def _links_again(synth, P, L_local, rank, dev):
+def _dist_check(rank, world, dev, group, exchange, tdist):
+    """A small problem, link-sharded over all ranks for 6 iterations (graph replays and eager iterations mixed), against
+    the same iterations on rank 0 alone: theta / p within 1e-10, replicas bit-identical."""
+    import numpy as np
     import torch
-    g1, g2, g3, lab = synth.planted_links_soa(P, L_local, seed=100 + rank, device=dev)
-    g1[:P] = torch.arange(P, dtype=torch.int32, device=dev)
-    return g1, g2, g3, 1 - lab, lab
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    rng = np.random.default_rng(3)
+    P, L, K = 500, 20000, 10
+    g = rng.integers(0, P, size=(L, 3)).astype(np.int32)
+    g[:P, 0] = np.arange(P)
+    lab = (rng.random(L) < 0.2).astype(np.int32)
+    # every rank draws DIFFERENT initial parameters: set_params must make rank 0's win everywhere
+    rr = np.random.default_rng(100 + rank)
+    theta = rr.dirichlet(np.ones(K), size=P)
+    pr = rr.random((K, K, K, 2))
+    pr /= pr.sum(axis=3, keepdims=True)
+    lo, hi = tdist.shard_bounds(L, rank, world)
+    eng = EMEngine(P, K, device=dev, group=group, exchange=exchange)
+    eng.set_train_links(g[lo:hi, 0], g[lo:hi, 1], g[lo:hi, 2], 1 - lab[lo:hi], lab[lo:hi])
+    eng.set_params(theta, pr)
+    eng.em_iterations(4)
+    eng.em_iteration()
+    eng.em_iterations(1)
+    th, p = eng.get_params()
+    chk = torch.from_numpy(np.concatenate([th.ravel(), p.ravel()])).to(dev)
+    allc = [torch.empty_like(chk) for _ in range(world)]
+    torch.distributed.all_gather(allc, chk, group=group)
+    same = all(torch.equal(c, allc[0]) for c in allc)
+    err = None
+    if rank == 0:
+        r0 = np.random.default_rng(100)
+        theta = r0.dirichlet(np.ones(K), size=P)
+        pr = r0.random((K, K, K, 2))
+        pr /= pr.sum(axis=3, keepdims=True)
+        one = EMEngine(P, K, device=dev)
+        one.set_train_links(g[:, 0], g[:, 1], g[:, 2], 1 - lab, lab)
+        one.set_params(theta, pr)
+        for _ in range(6):
+            one.em_iteration()
+        th1, p1 = one.get_params()
+        err = max(float(np.max(np.abs(th - th1) / np.maximum(np.abs(th1), 1e-300))),
+                  float(np.max(np.abs(p - p1) / np.maximum(np.abs(p1), 1e-300))))
+    ok = same and (err is None or err < 1e-10)
+    return {"status": "ok" if ok else "FAILED", "replicas_bit_identical": bool(same), "max_rel_err_vs_single_rank": err,
+            "what": "P=500, 20,000 links over %d ranks, 6 iterations (4 graph replays, 1 eager, 1 replay), ranks seeded "
+                    "differently; rank 0 recomputes alone" % world}
+
+
+def _cfg4(rank, world, dev, group, args, theta0, pr0, flush_l2, synth, tdist):
+    """BASELINE config 4: 6,000 genes x 1e8 triplets, K=10, link-sharded over the ranks (strong scaling)."""
+    import statistics as st
+    import torch
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    lo, hi = tdist.shard_bounds(CFG4_LINKS, rank, world)
+    L = hi - lo
+    eng = EMEngine(P_GENES, K_GROUPS, device=dev, group=group, exchange=args.exchange)
+    eng.set_train_links(*_links(synth, "uniform", P_GENES, L, 4000 + rank, dev))
+    torch.cuda.empty_cache()
+    eng.set_params(theta0, pr0)
+    eng.capture_graphs()
+    eng.set_params(theta0, pr0)
+    n = max(5, min(args.steps, 10))
+    for _ in range(3):
+        eng.graph_step()
+    tdist.barrier(group)
+    ms = _timed_replays(torch, eng, n, 0, flush_l2, dev)
+    tdist.barrier(group)
+    per = tdist.max_over_ranks(sum(ms), device=dev, group=group) / n
+    eng._check_peer()
+    out = {"value": CFG4_LINKS / (per * 1e-3), "unit": UNIT, "ms_per_step": per, "links_per_gpu": L, "links_total": CFG4_LINKS,
+           "steps": n, "scaling": "strong", "shape": "uniform",
+           "roofline_frac_6k3_over_dmma_peak": None}
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def _cfg3(rank, world, dev, group, synth, tdist):
+    """BASELINE config 3: 50 random restarts of cfg2 (800,000 training / 200,000 test triplets, K=10), restarts spread
+    round-robin over the ranks with no communication (run.sh:36-45); each restart is the reference's sample loop
+    (TIP.py:1253-1279: initialise from random.seed(1000 + s), iterate, likelihood check every 25 iterations after 100,
+    stop at |dL/L| < 0.01, then held-out likelihood, scores and metrics) through the drop-in Model."""
+    import random
+    import torch
+    from trigenicinteractionpredictor_b200 import TrigenicInteractionPredictor as tip
+    g1, g2, g3, n0, n1 = _links(synth, "kuzmin", P_GENES, L_PER_GPU + T_TEST, 100, dev)
+    tr = tuple(x[:L_PER_GPU].contiguous() for x in (g1, g2, g3, n0, n1))
+    te = tuple(x[L_PER_GPU:].contiguous() for x in (g1, g2, g3, n0, n1))
+    model = tip.Model(device=dev)
+    model.set_links_soa(tr, te, P=P_GENES)
+    mine = tdist.samples_for_rank(0, CFG3_SAMPLES, rank, world)
+    random.seed(999)
+    tip.train_sample(model, K_GROUPS, 130, 25, 100, verbose=False)        # warm-up restart: graphs, allocations
+    tdist.barrier(group)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    conv, iters, aucs = 0, 0, []
+    for s in mine:
+        random.seed(1000 + s)
+        ok, it, _ = tip.train_sample(model, K_GROUPS, 10000, 25, 100, verbose=False)
+        model.compute_likelihood('test')
+        model.calculate_test_set_results()
+        aucs.append(model.calculate_metrics()[3])
+        conv += int(ok)
+        iters += it
+    torch.cuda.synchronize(dev)
+    dt = tdist.max_over_ranks(time.perf_counter() - t0, device=dev, group=group)
+    tot = torch.tensor([conv, iters, len(mine)], dtype=torch.int64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(tot, group=group)
+    conv, iters, n = (int(x) for x in tot.tolist())
+    return {"samples_per_s": n / dt, "samples": n, "converged": conv, "seconds": dt, "em_iterations_total": iters,
+            "link_updates_per_s": iters * L_PER_GPU / dt, "samples_on_rank0": len(mine), "auc_rank0_first": aucs[0] if aucs else None,
+            "what": "50 restarts x (init on the host RNG, EM to convergence, held-out likelihood, scores, metrics); wall clock, max over ranks"}
 
 
 def _measure_peak(lib, kind):
-    import ctypes
     out = ctypes.c_double(0.0)
     rc = lib.tip_measure_fma_peak(kind, ctypes.byref(out))
     if rc != 0:
@@ -396,15 +624,14 @@ def _measure_peak(lib, kind):
     return out.value
 
 
-def _read_profile():
-    """dram traffic / fp64 pipe utilisation of the fused kernel from the committed ncu capture (per launch)."""
+def _read_profile(name):
+    """Per-launch figures of the dominant kernel from the committed ncu capture (profiles/<name>, written by
+    tools/ncu_metrics_json.py); `traffic` in the roofline is FROM THIS FILE, not measured in the run."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_em_fused_k10_metrics.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", name)) as fh:
             m = json.load(fh)
-        rd = float(m["dram__bytes_read.sum"][0]) * {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}[m["dram__bytes_read.sum"][1]]
-        wr = float(m["dram__bytes_write.sum"][0]) * {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}[m["dram__bytes_write.sum"][1]]
-        return {"traffic_bytes": rd + wr, "source": "profiles/r1_em_fused_k10_metrics.json",
-                "fp64_pipe_pct": float(m["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"][0])}
+        m["source"] = "profiles/" + name + " (ncu --set full capture, not measured in this run)"
+        return m
     except Exception:  # noqa: BLE001
         return {}
 
@@ -425,8 +652,8 @@ def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
     import torch
     from trigenicinteractionpredictor_b200 import _cabi
     P, K = eng.P, eng.K
-    rows_h = eng.train.rows.cpu().pin_memory()
     n_rows = eng.train.n_rows
+    rows_h = eng.train.rows[:n_rows].cpu().pin_memory()
     rows8_h = torch.empty(max(n_rows, 1), dtype=torch.int64).pin_memory()
     rc = lib.tip_rows_compact_host(rows_h.data_ptr(), n_rows, rows8_h.data_ptr())
     if rc != 0:
@@ -519,7 +746,9 @@ def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
         p_h.copy_(torch.from_numpy(np.ascontiguousarray(pr0)))
         dt16, dt, _ = run_both(False)
     if world == 1:
-        api = "tip_em_iterations_host (C ABI, pinned host buffers, 8-byte rows: TIP_ROWS_COMPACT8)"
+        api = ("tip_em_iterations_host (C ABI, pinned host buffers, 8-byte rows: TIP_ROWS_COMPACT8); one iteration per call, so "
+               "the K^3-per-link kernel that follows the rows' DMA front runs it (the slot-segmented kernels need the rows in "
+               "three orders, i.e. all of them on the device first)")
     else:
         api = ("EMEngine.em_iteration_host_rows: pinned host buffers, 8-byte rows, tip_em_step_host_rows follows the DMA "
                "front (link-sharded, %s exchange)" % args.exchange)
@@ -539,7 +768,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=["cfg2", "cfg4"], default="cfg2")
+    ap.add_argument("--shape", choices=["kuzmin", "uniform"], default="kuzmin",
+                    help="link shape of the headline workload (BASELINE config 2 names the Kuzmin-2018 shape)")
+    ap.add_argument("--skip", default="", help="comma list of legs to leave out: cfg4,cfg3,fp32,k3,e2e,cpu,dist_check")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
                     help="N>1: how link-shard statistics are summed (NVLink peer memory fused into the M-step, or NCCL)")

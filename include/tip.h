@@ -56,7 +56,8 @@ extern "C" {
 #define TIP_EM_SLOT_SEGMENTED 32u /* any K, fp64: all three theta statistics and the p statistic accumulated per run of
                                    equal gene, in three sort orders of the links (4K^2 FMA per link, no per-link atomics:
                                    hub genes cost nothing extra).  d_rows then holds the three orders back to back, n_rows
-                                   rows each: the packed rows, then tip_order_rows' output */
+                                   rows each, and the tile schedules behind them: the packed rows, then tip_order_rows'
+                                   output (tip_order_rows_out_bytes) */
 #define TIP_EM_GATHER_L1 64u     /* with TIP_EM_SLOT_SEGMENTED: gather the theta rows through L1 (cp.async.ca) instead of L2
                                    only.  For hub-shaped links (a few genes in most triplets): the hub rows then stay in
                                    L1 instead of being requested from a handful of L2 slices by every SM (measured 0.31 ->
@@ -93,8 +94,16 @@ int tip_pack_rows(const int32_t *d_g1, const int32_t *d_g2, const int32_t *d_g3,
  *      {gene of the ordering slot, slot-a gene (or slot-a for c), the remaining gene, position of the link in d_rows},
  *      i.e. {b, a, c, pos} and {c, a, b, pos}; padding rows are {0, 0, 0, -1}.  The rating blocks keep their sizes, so
  *      n_rows and n_rows_r0 describe all three orders.  Stable: links of one gene stay in slot-a order.
+ *      Behind the two orders, 3 * n_rows / 32 int32: the SCHEDULES of the two E-step launches (order a; orders b + c) -
+ *      chunks of up to four consecutive 32-row tiles, (first tile << 3) | tiles, sorted by descending cost (a tile costs
+ *      1 + the runs of equal gene that end in it; tiles with many runs stand alone and come first, single tiles close
+ *      the list), 0-terminated.  Hub-shaped links put tiles with 20-30 one-link runs next to thousands of tiles inside
+ *      one run; the schedule is what keeps every SM busy to the end of a launch.
+ *      d_rows_bc must hold tip_order_rows_out_bytes(n_rows) bytes and MUST directly follow the packed rows in memory
+ *      (d_rows_bc == d_rows + n_rows rows): tip_em_step takes one pointer to all of it.
  * Asynchronous on `stream`; digestion time, not iteration time. */
 int tip_order_rows_workspace_bytes(int64_t n_rows, size_t *bytes);
+int64_t tip_order_rows_out_bytes(int64_t n_rows);
 int tip_order_rows(const void *d_rows, int64_t n_rows, int64_t n_rows_r0, void *d_ws, size_t ws_bytes, void *d_rows_bc,
                    void *stream);
 
@@ -151,6 +160,14 @@ int tip_metrics_workspace_bytes(int64_t T, size_t *bytes);
 int tip_metrics(const double *d_scores, const int32_t *d_labels, int64_t T, int64_t positives_number,
                 void *d_ws, size_t ws_bytes, int64_t *d_out, void *stream);
 
+/* ---- Model.calculate_test_set_results, the ordering (TIP.py:568-569: results.sort(); results.reverse()) ----
+ * d_sorted[T] = the scores in descending order, d_order[T] = the test-set index of each (stable: equal scores keep their
+ * test order; the caller puts runs of EQUAL scores into the reference's (key string, label) order on the host - only
+ * those need the strings). */
+int tip_sort_scores_workspace_bytes(int64_t T, size_t *bytes);
+int tip_sort_scores(const double *d_scores, int64_t T, void *d_ws, size_t ws_bytes, int32_t *d_order, double *d_sorted,
+                    void *stream);
+
 /* ---- testResultsReducer.py:160-184: mean / median / standard deviation of every test triplet across samples ----
  * d_scores[S][T]: score of triplet t in sample j at [j * T + t]; d_n[t] (or NULL = S) = how many leading samples of
  * triplet t are valid.  mean = sequential sum in sample order / n; median = the reference's rule (ascending sort;
@@ -206,6 +223,18 @@ int tip_measure_fma_peak(int kind, double *tflops);
 /* scattered fp64 red.global.add throughput over `n_addr` doubles: G atomics/s in *gops.
  * mode 0: one random address per lane; mode 1: row-contiguous runs of 10 doubles. */
 int tip_measure_red_f64(int64_t n_addr, int mode, double *gops);
+
+/* gather bandwidth out of L2: random rows of `row_bytes` bytes (on 128-byte lines) of a table of n_rows_table rows, read
+ * with 16-byte L2-only loads by 2048 threads per SM - the access pattern of the slot-segmented passes.  GB/s of whole
+ * 32-byte sectors delivered in *gbs; the roofline denominator of those kernels. */
+int tip_measure_l2_gather(int n_rows_table, int row_bytes, double *gbs);
+
+/* ---- per-kernel timing of the slot-segmented E-step (measurement only) ----
+ * tip_seg3_timing(1): every following tip_em_step(TIP_EM_SLOT_SEGMENTED) records CUDA events on its stream between its
+ * five stages (not capturable in a CUDA graph while on); tip_seg3_last_timing waits for the last such step and returns
+ * the milliseconds of {workspace memset, prep kernel, pass A, pass B + C, finish kernel}. */
+int tip_seg3_timing(int enable);
+int tip_seg3_last_timing(float *h_ms5);
 
 #ifdef __cplusplus
 }

@@ -22,13 +22,20 @@ def main(out_dir):
     theta = rng.dirichlet(np.ones(K), size=P)
     pr = rng.random((K, K, K, 2))
     pr /= pr.sum(axis=3, keepdims=True)
+    # what each rank would draw from its own pid-seeded stream (the reference seeds with os.getpid(), TIP.py:1149): ranks
+    # other than 0 hand DIFFERENT parameters to set_params, which must make rank 0's copy the one everybody starts from
+    mine = np.random.default_rng(50 + rk)
+    theta_rk = theta if rk == 0 else mine.dirichlet(np.ones(K), size=P)
+    pr_rk = pr if rk == 0 else mine.random((K, K, K, 2))
     lo, hi = tdist.shard_bounds(L, rk, w)
     for exchange in ("nccl", "peer"):
         eng = EMEngine(P, K, device=dev, group=torch.distributed.group.WORLD, exchange=exchange)
         eng.set_train_links(g[lo:hi, 0], g[lo:hi, 1], g[lo:hi, 2], 1 - lab[lo:hi], lab[lo:hi])   # deg is allreduced inside
-        eng.set_params(theta, pr)
+        eng.set_params(theta_rk, pr_rk)
         print(rk, exchange, "links set", flush=True)
+        eng.em_iterations(3, use_graph=False)            # eager, graph replays and eager again: one parity counter
         eng.em_iterations(5, use_graph=True)
+        eng.em_iteration()
         th, p = eng.get_params()
         ll = eng.loglik("train")
         if eng.peer is not None:
@@ -39,7 +46,7 @@ def main(out_dir):
         ref = EMEngine(P, K, device=dev)
         ref.set_train_links(g[:, 0], g[:, 1], g[:, 2], 1 - lab, lab)
         ref.set_params(theta, pr)
-        for _ in range(5):
+        for _ in range(9):
             ref.em_iteration()
         th1, p1 = ref.get_params()
         np.savez(os.path.join(out_dir, "single.npz"), th=th1, p=p1, ll=ref.loglik("train"))

@@ -33,6 +33,11 @@ def _worker(rank, world, port, out_dir):
     deg = torch.from_numpy(np.bincount(ids[lo:hi].ravel(), minlength=dg.P))
     tdist.allreduce_sum_(deg)
     tdist.barrier()
+    # replicas must start from rank 0's parameters / seed whatever each rank drew (link shards)
+    mine = torch.full((5,), float(rank + 1), dtype=torch.float64)
+    tdist.broadcast_from_first_(mine)
+    assert torch.equal(mine, torch.ones(5, dtype=torch.float64))
+    assert tdist.broadcast_int(1234 + rank) == 1234
     mx = tdist.max_over_ranks(float(rank))
     s = stats.numpy()
     th, pr = orc.normalise_np(s[: nt.size].reshape(nt.shape), s[nt.size: nt.size + npr.size].reshape(npr.shape),

@@ -129,6 +129,36 @@ def test_shard_bounds_and_sample_assignment():
     assert sorted(s for r in range(8) for s in tdist.samples_for_rank(10, 50, r, 8)) == list(range(10, 60))
 
 
+def test_vectorised_soa_equals_the_per_link_loop():
+    """Model._soa parses all keys in one pass; it must give what splitting every key in a Python loop gives."""
+    from trigenicinteractionpredictor_b200.TrigenicInteractionPredictor import Model
+    rng = np.random.default_rng(4)
+    table = {}
+    for _ in range(5000):
+        a, b, c = rng.integers(0, 1200, 3).tolist()
+        table.setdefault("%d_%d_%d" % (a, b, c), [0, 0])[int(rng.integers(0, 2))] += 1
+    g1, g2, g3, n0, n1 = Model._soa(table)
+    assert all(x.dtype == np.int32 for x in (g1, g2, g3, n0, n1))
+    for i, (key, c) in enumerate(table.items()):
+        assert [int(g1[i]), int(g2[i]), int(g3[i])] == [int(t) for t in key.split("_")] and [int(n0[i]), int(n1[i])] == c
+    assert all(len(x) == 0 for x in Model._soa({}))
+
+
+def test_links_handed_over_as_arrays_behave_like_the_dict():
+    """Model.set_links_soa (how configs 3 and 4 enter the drop-in): links / test_links keep len, key order, values."""
+    from trigenicinteractionpredictor_b200.TrigenicInteractionPredictor import Model, SoALinks
+    g = np.array([[10, 11, 9], [3, 7, 5], [0, 2, 1]], dtype=np.int32)
+    n0, n1 = np.array([1, 0, 2], dtype=np.int32), np.array([0, 1, 1], dtype=np.int32)
+    m = Model()
+    m.set_links_soa((g[:, 0], g[:, 1], g[:, 2], n0, n1), (g[:1, 0], g[:1, 1], g[:1, 2], n0[:1], n1[:1]))
+    assert m.P == 12 and len(m.links) == 3 and len(m.test_links) == 1 and isinstance(m.links, SoALinks)
+    assert list(m.links.keys()) == ["10_11_9", "3_7_5", "0_2_1"] and list(m.links) == list(m.links.keys())
+    assert list(m.links.values()) == [[1, 0], [0, 1], [2, 1]]
+    assert dict(m.links.items())["3_7_5"] == [0, 1] and m.links.count_single_positive() == 2
+    got = Model._soa(m.links)
+    assert all(np.array_equal(a, b) for a, b in zip(got, (g[:, 0], g[:, 1], g[:, 2], n0, n1)))
+
+
 def test_product_never_touches_the_oracle_or_the_reference():
     """The oracle is test infrastructure: nothing under the package (nor the GPU arm of bench.py) may import it,
     read /root/reference, or carry a CPU fallback for the numerics."""

@@ -27,11 +27,52 @@ import sys
 
 import numpy as np
 
-__all__ = ["Model", "main"]
+__all__ = ["Model", "SoALinks", "main"]
 
 
 def _nested(arr: np.ndarray):
     return arr.tolist()
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+class SoALinks:
+    """Links handed over already digested (Model.set_links_soa): int32 arrays g1, g2, g3 in key slot order plus the
+    counts per rating, behind the read-only part of the dict interface the reference's `links` / `test_links` have
+    (len, iteration in order, keys "a_b_c" -> [n0, n1]).  Keys are formatted on demand, never stored: 1e8 links are
+    1.6 GB as arrays and would not fit a Python dict."""
+
+    def __init__(self, g1, g2, g3, n0, n1):
+        self.g = [x if _is_torch(x) else np.ascontiguousarray(x, dtype=np.int32) for x in (g1, g2, g3)]
+        self.n = [x if _is_torch(x) else np.ascontiguousarray(x, dtype=np.int32) for x in (n0, n1)]
+
+    def __len__(self):
+        return int(self.g[0].shape[0])
+
+    def _host(self):
+        return [x.cpu().numpy() if _is_torch(x) else x for x in self.g + self.n]
+
+    def keys(self):
+        a, b, c, _, _ = self._host()
+        for i in range(len(self)):
+            yield "%d_%d_%d" % (a[i], b[i], c[i])
+
+    __iter__ = keys
+
+    def values(self):
+        _, _, _, n0, n1 = self._host()
+        for i in range(len(self)):
+            yield [int(n0[i]), int(n1[i])]
+
+    def items(self):
+        return zip(self.keys(), self.values())
+
+    def count_single_positive(self):
+        """#{links with n1 == 1} (TIP.py:588)."""
+        n1 = self.n[1]
+        return int((n1 == 1).sum())
 
 
 class Model:
@@ -272,6 +313,22 @@ class Model:
         print('READ DATA train', len(self.links), len(self.nlinks))
         print('READ DATA test', len(self.test_links))
 
+    def set_links_soa(self, train, test=None, P=None):
+        """Addition (not in the reference): take links that are ALREADY digested - `train` / `test` = (g1, g2, g3, n0, n1)
+        int32 arrays (numpy, or torch tensors already on the device) of dense gene ids in the key's slot order (the
+        decimal-string order of TIP.py:353) and the counts per rating (TIP.py:361-368).  This is how BASELINE configs
+        3 and 4 enter the drop-in: 1e8 triplets cannot pass through the reference's dict of strings.  `links` and
+        `test_links` become read-only views with the dict's len / keys / values / items."""
+        self.links = SoALinks(*train)
+        self.test_links = SoALinks(*test) if test is not None else {}
+        if P is None:
+            tops = [int(x.max()) for x in self.links.g] + ([int(x.max()) for x in self.test_links.g] if test is not None else [])
+            P = max(tops) + 1
+        self.P = int(P)
+        self.id_gene = {}
+        self.gene_id = {}
+        self._links_version += 1
+
     # ------------------------------------------------------------------------------------------
     # 5-fold split (TIP.py:447-523) - bit-exact files, same global numpy stream
     # ------------------------------------------------------------------------------------------
@@ -308,13 +365,15 @@ class Model:
     @staticmethod
     def _soa(table):
         """dict {"a_b_c": [n0, n1]} (insertion order) -> int32 arrays g1,g2,g3,n0,n1."""
+        if isinstance(table, SoALinks):
+            return (*table.g, *table.n)
         n = len(table)
-        ids = np.empty((n, 3), dtype=np.int32)
-        cnt = np.empty((n, 2), dtype=np.int32)
-        for i, (key, c) in enumerate(table.items()):
-            a, b, d = key.split('_')
-            ids[i, 0], ids[i, 1], ids[i, 2] = int(a), int(b), int(d)
-            cnt[i, 0], cnt[i, 1] = c[0], c[1]
+        if n == 0:
+            z = np.empty(0, dtype=np.int32)
+            return z, z.copy(), z.copy(), z.copy(), z.copy()
+        # one pass in C instead of a Python loop per link: all keys joined, split once, parsed by numpy
+        ids = np.array("_".join(table.keys()).split("_"), dtype=np.int64).astype(np.int32).reshape(n, 3)
+        cnt = np.fromiter((c for pair in table.values() for c in pair), dtype=np.int32, count=2 * n).reshape(n, 2)
         return ids[:, 0].copy(), ids[:, 1].copy(), ids[:, 2].copy(), cnt[:, 0].copy(), cnt[:, 1].copy()
 
     def _ready(self, need_params=True):
@@ -333,7 +392,11 @@ class Model:
         eng = self._engine
         if self._packed_version != self._links_version:
             g1, g2, g3, n0, n1 = self._soa(self.links)
-            deg = np.bincount(np.concatenate([g1, g2, g3]), minlength=self.P).astype(np.int32)
+            if _is_torch(g1):
+                import torch
+                deg = torch.bincount(torch.cat([g1, g2, g3]).to(torch.int64), minlength=self.P).to(torch.int32)
+            else:
+                deg = np.bincount(np.concatenate([g1, g2, g3]), minlength=self.P).astype(np.int32)
             self._deg_zero = bool((deg[: self.P] == 0).any())
             if self._group is not None:
                 world, rk = _dist.world_size(self._group), _dist.rank(self._group)
@@ -403,21 +466,33 @@ class Model:
         self._results, self._results_stale = [], True
 
     def _build_results(self):
-        """[[score, "a_b_c", label], ...] sorted descending like list.sort(); reverse() (TIP.py:568-569)."""
-        scores = self._scores.cpu().numpy().tolist()
-        rows = []
-        for s, (key, n) in zip(scores, self.test_links.items()):
-            rows.append([s, key, 0 if n[0] else 1])
-        rows.sort()
-        rows.reverse()
+        """[[score, "a_b_c", label], ...] sorted descending like list.sort(); reverse() (TIP.py:568-569).  The order
+        comes from the device (tip_sort_scores: stable descending radix sort of the fp64 scores); only rows whose scores
+        are EQUAL - where the reference's list comparison falls through to the key string and the label - are put in
+        their reference order on the host."""
+        order, sorted_scores = self._engine.sort_scores(self._scores)
+        keys = list(self.test_links.keys())
+        labels = [0 if n[0] else 1 for n in self.test_links.values()]
+        rows = [[s, keys[i], labels[i]] for s, i in zip(sorted_scores.tolist(), order.tolist())]
+        ties = np.flatnonzero(sorted_scores[1:] == sorted_scores[:-1])
+        if ties.size:
+            starts = ties[np.concatenate([[True], np.diff(ties) > 1])]
+            for lo in starts.tolist():
+                hi = lo + 1
+                while hi < len(rows) and rows[hi][0] == rows[lo][0]:
+                    hi += 1
+                rows[lo:hi] = sorted(rows[lo:hi], reverse=True)
         self._results, self._results_stale = rows, False
 
     def calculate_metrics(self):
         n_train = len(self.links)
-        hits = 0
-        for n in self.links.values():
-            if n[1] == 1:                            # exactly one positive sighting (TIP.py:588)
-                hits += 1
+        if isinstance(self.links, SoALinks):
+            hits = self.links.count_single_positive()
+        else:
+            hits = 0
+            for n in self.links.values():
+                if n[1] == 1:                        # exactly one positive sighting (TIP.py:588)
+                    hits += 1
         positives_fraction = hits / n_train
         positives_number = int(positives_fraction * len(self.test_links))
         if self._scores is None or int(self._scores.numel()) == 0:
@@ -607,7 +682,13 @@ def main(argv=None):
         rk, world, local = _dist.init_from_env()
         if device is None:
             device = "cuda:%d" % local
-    random.seed(os.getpid() if seed is None else seed)
+    if seed is None and dist_mode == "links":
+        # link shards are replicas of ONE model: every rank must draw the same initial theta / p (TIP.py:1149 seeds
+        # with the pid, which differs per rank) - rank 0's pid is the seed of the whole job
+        seed_all = _dist.broadcast_int(os.getpid())
+        random.seed(seed_all)
+    else:
+        random.seed(os.getpid() if seed is None else seed)
 
     print("\n****************************************\n* Trigenic Interaction Predictor (B200) *\n"
           "****************************************\n\nDoing " + str(num_samples) + " samples of " + str(iterations) +

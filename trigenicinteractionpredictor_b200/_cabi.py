@@ -35,6 +35,7 @@ SIGNATURES = {
     "tip_pack_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t,
                               c_void_p, _pi64, _pi64, c_void_p, c_void_p]),
     "tip_order_rows_workspace_bytes": (c_int, [c_int64, _psz]),
+    "tip_order_rows_out_bytes": (c_int64, [c_int64]),
     "tip_order_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "tip_em_workspace_bytes": (c_int, [c_int, c_int, c_int64, c_uint, _psz]),
     "tip_em_step": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
@@ -48,6 +49,8 @@ SIGNATURES = {
     "tip_score": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tip_metrics_workspace_bytes": (c_int, [c_int64, _psz]),
     "tip_metrics": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "tip_sort_scores_workspace_bytes": (c_int, [c_int64, _psz]),
+    "tip_sort_scores": (c_int, [c_void_p, c_int64, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "tip_reduce_samples": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tip_em_iterations_host": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int,
                                        c_uint]),
@@ -59,6 +62,9 @@ SIGNATURES = {
     "tip_normalise_peers": (c_int, [c_int, c_int, ctypes.POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tip_measure_fma_peak": (c_int, [c_int, _pdbl]),
     "tip_measure_red_f64": (c_int, [c_int64, c_int, _pdbl]),
+    "tip_measure_l2_gather": (c_int, [c_int, c_int, _pdbl]),
+    "tip_seg3_timing": (c_int, [c_int]),
+    "tip_seg3_last_timing": (c_int, [ctypes.POINTER(ctypes.c_float)]),
 }
 
 

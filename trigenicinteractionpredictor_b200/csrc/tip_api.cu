@@ -447,6 +447,25 @@ __global__ void __launch_bounds__(256) red_probe_kernel(double *buf, int64_t n_a
     }
 }
 
+// random rows of a small (L2-resident) table, `vecs` 16-byte loads each, L2 only (ld.global.cg): the gather pattern of the
+// slot-segmented passes (theta rows of 8K bytes on 128-byte lines)
+__global__ void __launch_bounds__(256) gather_probe_kernel(const double2 *__restrict__ table, int n_rows_table, int row_vecs,
+                                                           int vecs, int iters, double *out)
+{
+    unsigned long long x = (blockIdx.x * 256ull + threadIdx.x) * 0x9E3779B97F4A7C15ull + 777;
+    double acc = 0.0;
+    for (int it = 0; it < iters; ++it) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        const double2 *row = table + (size_t)(x % (unsigned long long)n_rows_table) * row_vecs;
+        for (int v = 0; v < vecs; ++v) {
+            double2 d;
+            asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(d.x), "=d"(d.y) : "l"(row + v));
+            acc += d.x + d.y;
+        }
+    }
+    if (acc == 123456.789) out[0] = acc;
+}
+
 template <typename F>
 int time_kernel(F launch, double *ms_out)
 {
@@ -502,6 +521,28 @@ extern "C" int tip_measure_fma_peak(int kind, double *tflops)
     cudaFree(d_out);
     if (rc) return rc;
     *tflops = flops / (ms * 1e-3) / 1e12;
+    return 0;
+}
+
+extern "C" int tip_measure_l2_gather(int n_rows_table, int row_bytes, double *gbs)
+{
+    TIP_REQUIRE(gbs != nullptr && n_rows_table >= 1 && row_bytes >= 16 && row_bytes % 16 == 0 && row_bytes <= 1024,
+                "tip_measure_l2_gather: row_bytes must be a multiple of 16 up to 1024");
+    const int row_stride = (row_bytes + 127) / 128 * 128;
+    double2 *table = nullptr;
+    double *d_out = nullptr;
+    TIP_CHECK_CUDA(cudaMalloc(&table, (size_t)n_rows_table * row_stride));
+    TIP_CHECK_CUDA(cudaMemset(table, 0, (size_t)n_rows_table * row_stride));
+    TIP_CHECK_CUDA(cudaMalloc(&d_out, 256));
+    const int blocks = sm_count() * 8, threads = 256, iters = 512;
+    double ms = 0;
+    int rc = time_kernel([&] { gather_probe_kernel<<<blocks, threads>>>(table, n_rows_table, row_stride / 16, row_bytes / 16, iters, d_out); }, &ms);
+    cudaFree(table);
+    cudaFree(d_out);
+    if (rc) return rc;
+    // bytes that cross the L2 -> SM crossbar: whole 32-byte sectors of every row
+    const double sectors = (row_bytes + 31) / 32;
+    *gbs = sectors * 32.0 * (double)blocks * threads * iters / (ms * 1e-3) / 1e9;
     return 0;
 }
 

@@ -88,9 +88,53 @@ static size_t metrics_layout(int64_t T, void *base, MetWs *ws)
     return off + 256;
 }
 
+__global__ void iota_kernel(int32_t *v, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = (int32_t)i;
+}
+
+static size_t sort_scores_layout(int64_t T, size_t *o_idx, size_t *o_cub, size_t *cub_bytes)
+{
+    size_t cb = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, cb, (const double *)nullptr, (double *)nullptr, (const int32_t *)nullptr,
+                                              (int32_t *)nullptr, T, 0, 64, (cudaStream_t)0);
+    *o_idx = 0;
+    *o_cub = a256((size_t)T * 4);
+    *cub_bytes = cb;
+    return *o_cub + a256(cb) + 256;
+}
+
 }  // namespace tip
 
 using namespace tip;
+
+extern "C" int tip_sort_scores_workspace_bytes(int64_t T, size_t *bytes)
+{
+    TIP_REQUIRE(T >= 0 && bytes != nullptr, "tip_sort_scores_workspace_bytes: bad arguments");
+    size_t a, b, c;
+    *bytes = sort_scores_layout(T < 1 ? 1 : T, &a, &b, &c);
+    return 0;
+}
+
+extern "C" int tip_sort_scores(const double *d_scores, int64_t T, void *d_ws, size_t ws_bytes, int32_t *d_order,
+                               double *d_sorted, void *stream)
+{
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TIP_REQUIRE(T >= 0 && T < (1ll << 31), "tip_sort_scores: T out of range");
+    if (T == 0) return 0;
+    size_t o_idx, o_cub, cub_bytes;
+    const size_t need = sort_scores_layout(T, &o_idx, &o_cub, &cub_bytes);
+    TIP_REQUIRE(d_scores && d_order && d_sorted && d_ws && ws_bytes >= need, "tip_sort_scores: workspace too small (%zu < %zu)",
+                ws_bytes, need);
+    char *base = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(d_ws) + 255) / 256 * 256);
+    int32_t *idx = reinterpret_cast<int32_t *>(base + o_idx);
+    const int64_t want = (T + 255) / 256;
+    iota_kernel<<<(int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8), 256, 0, st>>>(idx, T);
+    TIP_CHECK_CUDA(cudaGetLastError());
+    size_t cb = cub_bytes;
+    TIP_CHECK_CUDA(cub::DeviceRadixSort::SortPairsDescending(base + o_cub, cb, d_scores, d_sorted, idx, d_order, T, 0, 64, st));
+    return 0;
+}
 
 extern "C" int tip_metrics_workspace_bytes(int64_t T, size_t *bytes)
 {

@@ -41,6 +41,9 @@ __global__ void peer_barrier_kernel(FlagPtrs flags, unsigned long long *epoch, i
     __shared__ unsigned long long e;
     if (threadIdx.x == 0) e = *epoch + 1;
     __syncthreads();
+    // a barrier that timed out poisons the epoch (~0) FOR GOOD: later barriers neither signal nor pass, so the peers time
+    // out as well and every rank's host-side check (PeerExchange.check) raises - never a silent wrap-around to epoch 0
+    if (e == 0ull) return;
     __threadfence_system();  // this rank's statistics (written by earlier kernels of the stream) are visible to peers
     const int t = threadIdx.x;
     __shared__ int timed_out;

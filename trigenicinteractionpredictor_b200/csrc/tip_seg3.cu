@@ -20,7 +20,15 @@
 // TRANSPOSED in shared memory ([component][link], stride 36 doubles: fragment loads and the lane = link stores are
 // both conflict-free).  Accumulator fragments stay in registers across tiles and are flushed (red.global.add.f64)
 // only where the run of equal gene ends or the warp's chunk of tiles ends: atomics per iteration ~ K^2 x (#runs +
-// #chunks) instead of 2 K x #links.  Tiles are handed out dynamically (atomic chunk counter) to single-warp CTAs.
+// #chunks) instead of 2 K x #links.
+//
+// Scheduling.  A tile's cost grows with the number of runs it holds (every run end is a flush and a Z fetch), and
+// hub-shaped links put tiles with 20-30 one-link runs (array genes that appear once or twice in a slot) next to thousands
+// of tiles inside one hub run: handing out consecutive tiles left a few warps with ten such tiles each and the SMs idle
+// for 70 % of the kernel (ncu: 354k cycles elapsed, 100k active).  tip_order_rows therefore writes a SCHEDULE per
+// launch - chunks of up to four consecutive tiles, tiles with many runs on their own, sorted by descending cost, single
+// tiles at the very end - and the single-warp CTAs draw chunk after chunk from one atomic counter (longest processing time
+// first; two draws in flight per warp).
 #include <stdlib.h>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -75,8 +83,9 @@ struct S3Args {
     const double *Zg;        // [2][P][KK]            (pass A)
     double *sbuf;            // [tiles_per_order * 32] (written by pass A, read by pass BC)
     double *Mg;              // [3][2][P][KK]
-    unsigned *counter;       // tile counter of this launch, zero on entry
-    int chunk;               // most tiles per draw
+    unsigned *counter;       // schedule position counter of this launch, zero on entry
+    const int *sched;        // chunks of this launch: (first tile << 3) | tiles, by descending cost; 0 = end of the list
+    int n_sched;             // entries in sched (real chunks first, zeros behind them)
     int tune;                // bit 0: gather through L1 (cp.async.ca) instead of L2 only (.cg)
 };
 
@@ -142,7 +151,7 @@ __device__ __forceinline__ void s3_gather(const double *__restrict__ theta, cons
 
 // NST stage buffers: the gathers of the next NST - 1 tiles are in flight while a tile is computed
 template <int K, bool FIRST, int NST, bool CA>
-__global__ void __launch_bounds__(32) seg3_pass_kernel(const S3Args a)
+__global__ void __launch_bounds__(32, K <= 16 ? (FIRST ? 16 : 18) : 1) seg3_pass_kernel(const S3Args a)
 {
     using C = S3<K>;
     constexpr int KK = C::KK, NB = C::NB, NKG = C::NKG, RS = C::RS, D = NST - 1;
@@ -181,41 +190,32 @@ __global__ void __launch_bounds__(32) seg3_pass_kernel(const S3Args a)
         return ((a.slot0 + so) * 2 + (tl >= a.n_tiles_r0 ? 1 : 0)) * a.P;
     };
 
-    // ---- tile sequence of this warp: chunks of consecutive tiles drawn from one atomic counter, guided self-scheduling:
-    // a draw asks for (remaining tiles) / (2 x warps), at most a.chunk and at least one tile - long chunks while there is
-    // plenty of work (few same-address atomics, which serialise in one L2 slice at about a nanosecond each, and few
-    // accumulator flushes), single tiles at the end (no tail).  Two draws are kept in flight per warp: the counter's
-    // round trip is a microsecond under load.
+    // ---- tile sequence of this warp: chunks of the schedule, drawn from one atomic counter.  Lane 0 keeps one schedule
+    // entry loaded (`ent`, the next chunk) and one position drawn ahead (`pos2`): the counter's round trip and the entry's
+    // load both have a whole chunk of compute to return.
     int gen_t = 0, gen_end = 0;
     bool gen_done = false;
-    unsigned pend = 0, pend_w = 0, pend2 = 0, pend2_w = 0;   // (first tile, tiles asked for) of the draws in flight; lane 0
-    auto guided = [&](unsigned pos) -> unsigned {
-        const unsigned rem = pos < (unsigned)a.n_tiles ? (unsigned)a.n_tiles - pos : 0u;
-        unsigned w = rem / (2u * gridDim.x);
-        w = w > (unsigned)a.chunk ? (unsigned)a.chunk : w;
-        return w < 1u ? 1u : w;
-    };
+    unsigned pos2 = 0;
+    int ent = 0;
     if (lane == 0) {
-        pend_w = pend2_w = guided(0u);
-        pend = atomicAdd(a.counter, pend_w);
-        pend2 = atomicAdd(a.counter, pend2_w);
+        const unsigned p0 = atomicAdd(a.counter, 1u);
+        pos2 = atomicAdd(a.counter, 1u);
+        ent = p0 < (unsigned)a.n_sched ? __ldg(a.sched + p0) : 0;
     }
     auto next_tile = [&]() -> int {
         if (gen_t < gen_end) return gen_t++;
         if (gen_done) return -1;
-        const unsigned t0 = __shfl_sync(0xffffffffu, pend, 0), w = __shfl_sync(0xffffffffu, pend_w, 0);
-        if (t0 >= (unsigned)a.n_tiles) {
+        const int e = __shfl_sync(0xffffffffu, ent, 0);
+        if (e == 0) {
             gen_done = true;
             return -1;
         }
-        pend = pend2;
-        pend_w = pend2_w;
         if (lane == 0) {
-            pend2_w = guided(t0 + w);
-            pend2 = atomicAdd(a.counter, pend2_w);
+            ent = pos2 < (unsigned)a.n_sched ? __ldg(a.sched + pos2) : 0;
+            pos2 = atomicAdd(a.counter, 1u);
         }
-        gen_t = (int)t0;
-        gen_end = (t0 + w < (unsigned)a.n_tiles) ? (int)(t0 + w) : a.n_tiles;
+        gen_t = e >> 3;
+        gen_end = gen_t + (e & 7);
         return gen_t++;
     };
     auto issue_gather = [&](int buf, const int4 &me) {
@@ -634,17 +634,6 @@ static int s3_skip()
     return v;
 }
 
-static int s3_chunk_tiles()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("TIP_SEG3_CHUNK");
-        v = e ? atoi(e) : 8;
-        if (v < 1) v = 1;
-    }
-    return v;
-}
-
 // stage buffers per warp: TIP_SEG3_STAGES_A / TIP_SEG3_STAGES_BC = 1 | 2 (1: no gather prefetch inside a warp, most warps per SM)
 static int s3_stages(bool first)
 {
@@ -655,6 +644,20 @@ static int s3_stages(bool first)
         if (v[first] != 1 && v[first] != 2) v[first] = 2;
     }
     return v[first];
+}
+
+// Per-kernel timing of one E-step (tip_seg3_timing): CUDA events recorded on the launching stream between the five
+// stages.  Off by default (event records cannot be captured in a CUDA graph); bench.py switches it on around the
+// un-graphed steps it uses for the roofline of the dominant kernel.
+static bool g_s3_timing = false;
+static cudaEvent_t g_s3_ev[6] = {};
+static int s3_mark(int i, cudaStream_t st)
+{
+    if (!g_s3_timing) return 0;
+    if (!g_s3_ev[0])
+        for (int j = 0; j < 6; ++j) TIP_CHECK_CUDA(cudaEventCreate(&g_s3_ev[j]));
+    TIP_CHECK_CUDA(cudaEventRecord(g_s3_ev[i], st));
+    return 0;
 }
 
 template <int K, bool FIRST, int NST, bool CA>
@@ -694,11 +697,13 @@ static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_r
 {
     const S3Layout l = s3_layout(P, K, n_rows);
     const int KK = K * K;
-    TIP_REQUIRE(n_rows / 32 < (1ll << 29), "tip_em_step: too many tiles in one shard for the slot-segmented kernels");
+    TIP_REQUIRE(n_rows / 32 < (1ll << 27), "tip_em_step: too many tiles in one shard for the slot-segmented kernels");
     // M and the chunk counters start from zero
     const int skip = s3_skip();
+    if (s3_mark(0, st)) return -2;
     if (!(skip & 1)) TIP_CHECK_CUDA(cudaMemsetAsync(ws + l.off_M, 0, sizeof(double) * (l.off_cnt + kS3CounterDoubles), st));
     else TIP_CHECK_CUDA(cudaMemsetAsync(ws + l.off_cnt, 0, sizeof(double) * kS3CounterDoubles, st));
+    if (s3_mark(1, st)) return -2;
     if (!(skip & 2)) {
         const size_t smem = sizeof(double) * ((K <= 20 ? 2 * KK * K : 0) + kPrepGenes * K);
         static bool attr = false;
@@ -719,19 +724,26 @@ static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_r
     a.Zg = ws + l.off_Z;
     a.sbuf = ws + l.off_s;
     a.Mg = ws + l.off_M;
-    a.chunk = s3_chunk_tiles();
     a.tune = s3_tune() | (gather_l1 ? 1 : 0);
     a.n_tiles = a.tiles_per_order;
     a.slot0 = 0;
     a.counter = reinterpret_cast<unsigned *>(ws + l.off_cnt);
+    const int *sched = reinterpret_cast<const int *>(rows + 3 * n_rows);   // written by tip_order_rows behind the three orders
+    a.sched = sched;
+    a.n_sched = a.tiles_per_order;
+    if (s3_mark(2, st)) return -2;
     int rc = (skip & 4) ? 0 : s3_launch_pass<K, true>(a, st);
     if (rc) return rc;
+    if (s3_mark(3, st)) return -2;
     a.rows = rows + n_rows;
     a.n_tiles = 2 * a.tiles_per_order;
     a.slot0 = 1;
     a.counter = reinterpret_cast<unsigned *>(ws + l.off_cnt) + kS3Groups * 32;
+    a.sched = sched + a.tiles_per_order;
+    a.n_sched = 2 * a.tiles_per_order;
     rc = (skip & 8) ? 0 : s3_launch_pass<K, false>(a, st);
     if (rc) return rc;
+    if (s3_mark(4, st)) return -2;
     if (!(skip & 16)) {
         constexpr int NBC = (K * K + 7) / 8;
         const int n_tasks = ((P + 7) / 8) * 3 + 2 * NBC * ((P + kFin3GeneChunk - 1) / kFin3GeneChunk);
@@ -739,10 +751,11 @@ static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_r
         seg3_finish_kernel<K><<<(n_tasks + wpc - 1) / wpc, kFin3Threads, 0, st>>>(P, theta, ws + l.off_PT, ws + l.off_M, stats);
         TIP_CHECK_CUDA(cudaGetLastError());
     }
+    if (s3_mark(5, st)) return -2;
     return 0;
 }
 
-// rows: order a | order b | order c, n_rows rows each (tip_order_rows); stats zeroed by the caller
+// rows: order a | order b | order c, n_rows rows each, then the two schedules (tip_order_rows); stats zeroed by the caller
 int launch_em_seg3(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
                    double *stats, double *ws, bool gather_l1, cudaStream_t st)
 {
@@ -788,6 +801,67 @@ __global__ void order_emit_kernel(const int4 *__restrict__ rows, const int32_t *
     }
 }
 
+// ---- the schedule of a launch (see the header comment).  One warp per group of kSchedGroup consecutive tiles of the
+// launch's tile sequence (order a; or order b followed by order c).  A tile's cost = 1 + run ends inside it, where a run
+// ends wherever (slot, rating, gene) changes - exactly what the pass kernel compares.  Every group owns kSchedGroup
+// slots of the (key, entry) arrays: a light group fills one (the whole group as one chunk), a group with a heavy tile,
+// or one of the groups set aside for the end of the list, fills one per tile; unused slots stay (0, 0).  The arrays are
+// then sorted by descending key: heavy tiles first (longest processing time first), chunks by cost, single tiles last.
+constexpr int kSchedGroup = 4;        // tiles per chunk (an entry holds the count in 3 bits)
+constexpr int kSchedHeavy = 6;        // a tile with at least this many run ends is scheduled on its own
+constexpr int kSchedTailTiles = 8 * 148 * 16;   // about this many tiles are handed out one by one at the end
+
+__global__ void __launch_bounds__(128) sched_build_kernel(const int4 *__restrict__ rows, int n_tiles, int tiles_per_order,
+                                                          int n_tiles_r0, int tail_stride, unsigned *__restrict__ keys,
+                                                          int *__restrict__ vals)
+{
+    const int lane = threadIdx.x & 31;
+    const int n_groups = (n_tiles + kSchedGroup - 1) / kSchedGroup;
+    for (int g = blockIdx.x * 4 + (threadIdx.x >> 5); g < n_groups; g += gridDim.x * 4) {
+        int cost[kSchedGroup];
+        int heavy = 0, total = 0, nt = 0;
+#pragma unroll
+        for (int j = 0; j < kSchedGroup; ++j) {
+            const int t = g * kSchedGroup + j;
+            cost[j] = 0;
+            if (t < n_tiles) {
+                auto key_of = [&](int64_t row) -> long long {
+                    const int tt = (int)(row >> 5);
+                    const int so = tt >= tiles_per_order ? 1 : 0, tl = tt - (so ? tiles_per_order : 0);
+                    return ((long long)(so * 2 + (tl >= n_tiles_r0 ? 1 : 0)) << 32) | (unsigned)rows[row].x;
+                };
+                const int64_t row = (int64_t)t * 32 + lane;
+                const long long k = key_of(row);
+                const long long kp = row > 0 ? key_of(row - 1) : k;
+                const int b = __popc(__ballot_sync(0xffffffffu, k != kp));
+                cost[j] = 1 + b;
+                total += b;
+                heavy |= b >= kSchedHeavy;
+                ++nt;
+            }
+        }
+        if (lane == 0) {
+            const bool tail = (g % tail_stride) == tail_stride - 1;
+#pragma unroll
+            for (int j = 0; j < kSchedGroup; ++j) {
+                unsigned key = 0;
+                int val = 0;
+                const int t = g * kSchedGroup + j;
+                if (heavy) {
+                    if (j < nt) { key = 128u + (unsigned)cost[j]; val = (t << 3) | 1; }
+                } else if (tail) {
+                    if (j < nt) { key = (unsigned)cost[j]; val = (t << 3) | 1; }
+                } else if (j == 0) {
+                    key = 64u + (unsigned)(1 + total);
+                    val = ((g * kSchedGroup) << 3) | nt;
+                }
+                keys[g * kSchedGroup + j] = key;
+                vals[g * kSchedGroup + j] = val;
+            }
+        }
+    }
+}
+
 static size_t order_layout(int64_t n, size_t *o_ki, size_t *o_ko, size_t *o_vi, size_t *o_vo, size_t *o_cub, size_t *cub_bytes)
 {
     size_t cb = 0;
@@ -807,6 +881,20 @@ static size_t order_layout(int64_t n, size_t *o_ki, size_t *o_ko, size_t *o_vi, 
 }  // namespace tip
 
 using namespace tip;
+
+extern "C" int tip_seg3_timing(int enable)
+{
+    g_s3_timing = enable != 0;
+    return 0;
+}
+
+extern "C" int tip_seg3_last_timing(float *h_ms5)
+{
+    TIP_REQUIRE(h_ms5 != nullptr && g_s3_ev[0] != nullptr, "tip_seg3_last_timing: no timed slot-segmented E-step has run");
+    TIP_CHECK_CUDA(cudaEventSynchronize(g_s3_ev[5]));
+    for (int i = 0; i < 5; ++i) TIP_CHECK_CUDA(cudaEventElapsedTime(h_ms5 + i, g_s3_ev[i], g_s3_ev[i + 1]));
+    return 0;
+}
 
 extern "C" int tip_order_rows_workspace_bytes(int64_t n_rows, size_t *bytes)
 {
@@ -842,5 +930,28 @@ extern "C" int tip_order_rows(const void *d_rows, int64_t n_rows, int64_t n_rows
         order_emit_kernel<<<grid, 256, 0, st>>>(rows, vo, n_rows, slot, out + (slot - 1) * n_rows);
         TIP_CHECK_CUDA(cudaGetLastError());
     }
+    // the schedules of the two launches, behind the orders: [T] for order a, [2T] for orders b + c
+    const int T = (int)(n_rows / 32), r0 = (int)(n_rows_r0 / 32);
+    int *sched = reinterpret_cast<int *>(out + 2 * n_rows);
+    for (int launch = 0; launch < 2; ++launch) {
+        const int nt = launch == 0 ? T : 2 * T;
+        const int n_groups = (nt + kSchedGroup - 1) / kSchedGroup, n_slots = n_groups * kSchedGroup;
+        int tail_stride = n_groups / (kSchedTailTiles / kSchedGroup);
+        if (tail_stride < 4) tail_stride = 4;
+        const int want_b = (n_groups + 3) / 4;
+        sched_build_kernel<<<want_b < sm_count() * 16 ? want_b : sm_count() * 16, 128, 0, st>>>(
+            launch == 0 ? rows : out, nt, T, r0, tail_stride, ki, vi);
+        TIP_CHECK_CUDA(cudaGetLastError());
+        size_t cb = cub_bytes;
+        TIP_CHECK_CUDA(cub::DeviceRadixSort::SortPairsDescending(base + o_cub, cb, ki, ko, vi, vo, n_slots, 0, 8, st));
+        // the first nt sorted entries hold every real chunk (there are at most nt of them); zeros follow
+        TIP_CHECK_CUDA(cudaMemcpyAsync(sched + (launch == 0 ? 0 : T), vo, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToDevice, st));
+    }
     return 0;
+}
+
+extern "C" int64_t tip_order_rows_out_bytes(int64_t n_rows)
+{
+    if (n_rows < 0) return -1;
+    return 2 * n_rows * 16 + 3 * (n_rows / 32) * 4 + 16;
 }

@@ -62,6 +62,24 @@ def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
     return t
 
 
+def broadcast_from_first_(t: torch.Tensor, group=None) -> torch.Tensor:
+    """In place: every rank of `group` receives the tensor of the group's first rank; a no-op in a single process."""
+    if world_size(group) > 1:
+        src = td.get_global_rank(group, 0) if group is not None and group is not td.group.WORLD else 0
+        td.broadcast(t, src=src, group=group)
+    return t
+
+
+def broadcast_int(value: int, group=None) -> int:
+    """The integer rank 0 holds, on every rank (e.g. the seed of a link-sharded run)."""
+    if world_size(group) == 1:
+        return int(value)
+    box = [int(value)]
+    td.broadcast_object_list(box, src=td.get_global_rank(group, 0) if group is not None and group is not td.group.WORLD else 0,
+                             group=group)
+    return int(box[0])
+
+
 def barrier(group=None):
     if world_size(group) > 1:
         td.barrier(group=group)
@@ -119,4 +137,5 @@ class PeerExchange:
     def check(self):
         """Raises if a barrier timed out (a peer stopped participating)."""
         if int(self.epoch.item()) == -1:
-            raise RuntimeError("tip_peer_barrier timed out: a peer rank stopped participating")
+            raise RuntimeError("tip_peer_barrier timed out: a peer rank stopped participating; the statistics of that "
+                               "iteration were incomplete and the parameters since then are invalid")

@@ -11,6 +11,7 @@ CUDA kernels behind the C ABI (include/tip.h).  There is no CPU path.
 from __future__ import annotations
 
 import ctypes
+import functools
 
 import numpy as np
 import torch
@@ -18,9 +19,23 @@ import torch
 from . import _cabi
 from . import dist as _dist
 
+# libtip.so keeps per-process caches that belong to ONE device (SM count, function attributes, the constant-bank
+# staging buffer, events, the host-entry scratch): one CUDA device per process, the first engine decides which.
+_PROCESS_DEVICE = None
+
 
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _on_device(fn):
+    """Run a method with the engine's device current: libtip launches on the CURRENT device (a default-stream handle
+    of 0 carries no device), so every call into it must be made with `self.device` selected."""
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
 
 
 class PackedLinks:
@@ -29,6 +44,7 @@ class PackedLinks:
     def __init__(self, rows, n_rows, n_rows_r0, n_real, deg):
         self.rows, self.n_rows, self.n_rows_r0, self.n_real, self.deg = rows, n_rows, n_rows_r0, n_real, deg
         self.rows3 = None     # slot-a | slot-b | slot-c orders back to back (tip_order_rows); rows is then its first third
+        self.rows3_buf = None  # the buffer behind rows3: the three orders, then the tile schedules
 
 
 def default_flags(K: int) -> int:
@@ -45,6 +61,15 @@ class EMEngine:
         self.lib = _cabi.load()
         self.P, self.K = int(P), int(K)
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        global _PROCESS_DEVICE
+        if _PROCESS_DEVICE is None:
+            _PROCESS_DEVICE = self.device.index
+        elif _PROCESS_DEVICE != self.device.index:
+            raise _cabi.TipLibraryError(
+                "libtip.so holds per-process state of cuda:%d; a second device (cuda:%d) in the same process is not "
+                "supported - run one process per GPU (torchrun / --dist)" % (_PROCESS_DEVICE, self.device.index))
         self.group = group
         self._auto_flags = flags is None
         self.flags = default_flags(int(K)) if flags is None else int(flags)
@@ -79,6 +104,7 @@ class EMEngine:
             return a.to(device=self.device, dtype=torch.int32).contiguous()
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
 
+    @_on_device
     def pack(self, g1, g2, g3, n0, n1, want_deg=True) -> PackedLinks:
         """tip_pack_rows: SoA -> rows ordered (rating, slot-a gene) in 32-row single-rating tiles."""
         g1, g2, g3, n0, n1 = (self._as_dev_i32(x) for x in (g1, g2, g3, n0, n1))
@@ -99,6 +125,7 @@ class EMEngine:
             rows = rows[: n_rows.value].clone() if n_rows.value < rows.shape[0] else rows
         return PackedLinks(rows, int(n_rows.value), int(part[0]), int(part[2]), deg)
 
+    @_on_device
     def order_rows(self, links: PackedLinks):
         """tip_order_rows: append the slot-b and slot-c orders of the packed rows (TIP_EM_SLOT_SEGMENTED)."""
         n = links.n_rows
@@ -106,14 +133,18 @@ class EMEngine:
             nb = ctypes.c_size_t(0)
             _cabi.check(self.lib.tip_order_rows_workspace_bytes(n, ctypes.byref(nb)), "tip_order_rows_workspace_bytes")
             ws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
-            rows3 = torch.empty((3 * n, 4), dtype=torch.int32, device=self.device)
+            # one buffer: order a | order b | order c | schedules of the two launches
+            n_i32 = 4 * n + (int(self.lib.tip_order_rows_out_bytes(n)) + 3) // 4
+            flat = torch.empty(n_i32, dtype=torch.int32, device=self.device)
+            rows3 = flat[: 12 * n].view(3 * n, 4)
             rows3[:n].copy_(links.rows[:n])
-            _cabi.check(self.lib.tip_order_rows(_ptr(rows3), n, links.n_rows_r0, _ptr(ws), nb.value,
-                                                ctypes.c_void_p(rows3.data_ptr() + n * 16), self._stream()), "tip_order_rows")
-            self.launches += 4
+            _cabi.check(self.lib.tip_order_rows(_ptr(flat), n, links.n_rows_r0, _ptr(ws), nb.value,
+                                                ctypes.c_void_p(flat.data_ptr() + n * 16), self._stream()), "tip_order_rows")
+            self.launches += 10
             torch.cuda.current_stream(self.device).synchronize()
-        links.rows3, links.rows = rows3, rows3[:n]
+        links.rows3, links.rows, links.rows3_buf = rows3, rows3[:n], flat
 
+    @_on_device
     def set_train_links(self, g1, g2, g3, n0, n1, global_deg=None):
         """This rank's shard of the training links.  `deg` (distinct links per gene, TIP.py:986-994) is
         summed over shards unless the caller supplies the global vector."""
@@ -139,24 +170,34 @@ class EMEngine:
             self.em_ws_bytes = nb.value
         self._graphs = None
 
+    @_on_device
     def set_test_links(self, g1, g2, g3, n0, n1):
         self.test = self.pack(g1, g2, g3, n0, n1, want_deg=False)
         g1, g2, g3, n0 = (self._as_dev_i32(x) for x in (g1, g2, g3, n0))
         labels = (n0 == 0).to(torch.int32)            # TIP.py:560-563: 0 if n0 else 1
         self.test_ids = (g1, g2, g3, labels)
 
+    @_on_device
     def degrees(self) -> np.ndarray:
         return self.train.deg.cpu().numpy()
 
     # ------------------------------------------------------------------ parameters
+    @_on_device
     def set_params(self, theta, p):
         th = torch.from_numpy(np.ascontiguousarray(theta, dtype=np.float64).reshape(-1))
         pp = torch.from_numpy(np.ascontiguousarray(p, dtype=np.float64).reshape(-1))
         assert th.numel() == self.P * self.K and pp.numel() == 2 * self.K ** 3
         self.theta.copy_(th, non_blocking=False)
         self.p.copy_(pp, non_blocking=False)
+        if self.world > 1:
+            # link shards: every rank must start from the SAME parameters (p is updated multiplicatively from the
+            # local copy, so replicas that start apart never meet again): rank 0's copy wins
+            _dist.broadcast_from_first_(self.theta, self.group)
+            _dist.broadcast_from_first_(self.p, self.group)
 
+    @_on_device
     def get_params(self):
+        self._check_peer()
         return (self.theta.cpu().numpy().reshape(self.P, self.K),
                 self.p.cpu().numpy().reshape(self.K, self.K, self.K, 2))
 
@@ -164,6 +205,21 @@ class EMEngine:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _check_peer(self):
+        """Called wherever the host synchronises with the device: a peer barrier that timed out poisons the epoch
+        (the statistics of that iteration were incomplete) - raise instead of carrying on with a wrong model."""
+        if self.peer is not None:
+            self.peer.check()
+
+    def _peer_mstep(self, par):
+        _cabi.check(self.lib.tip_peer_barrier(self.peer.flag_ptrs, _ptr(self.peer.epoch), self.peer.rank,
+                                              self.peer.world, self._stream()), "tip_peer_barrier")
+        _cabi.check(self.lib.tip_normalise_peers(self.P, self.K, self.peer.stats_ptrs[par], self.peer.world,
+                                                 _ptr(self.train.deg), _ptr(self.theta), _ptr(self.p),
+                                                 self._stream()), "tip_normalise_peers")
+        self.launches += 2
+
+    @_on_device
     def em_step(self, stats=None):
         """E-step statistics of this rank's rows into `stats` (default self.stats); no normalisation."""
         t = self.train
@@ -177,6 +233,7 @@ class EMEngine:
         else:
             self.launches += 3 if (self.K > 4 and not (self.flags & _cabi.TIP_EM_FORCE_GENERIC)) else 2
 
+    @_on_device
     def em_step_host_rows(self, h_rows: torch.Tensor, compact: bool, stats=None):
         """E-step of this rank's rows read from PINNED HOST memory (16-byte rows, or the 8-byte rows of
         tip_rows_compact_host): one copy on a side stream, the fused kernel follows the DMA front
@@ -197,6 +254,7 @@ class EMEngine:
             ctypes.c_void_p(self._copy_stream.cuda_stream)), "tip_em_step_host_rows")
         self.launches += 3 if self.K > 4 else 2
 
+    @_on_device
     def host_rows_arrived(self) -> bool:
         """False when a streamed E-step gave up waiting for its rows (synchronises)."""
         bad = int(self._stream_err[0].item()) != 0
@@ -204,67 +262,65 @@ class EMEngine:
             self._stream_err.zero_()
         return not bad
 
+    @_on_device
     def em_iteration_host_rows(self, h_rows: torch.Tensor, compact: bool):
         """em_iteration() with the E-step reading its rows from pinned host memory."""
         if self.peer is not None:
             par = self._iter & 1
             self._iter += 1
             self.em_step_host_rows(h_rows, compact, self.peer.stats(par))
-            _cabi.check(self.lib.tip_peer_barrier(self.peer.flag_ptrs, _ptr(self.peer.epoch), self.peer.rank,
-                                                  self.peer.world, self._stream()), "tip_peer_barrier")
-            _cabi.check(self.lib.tip_normalise_peers(self.P, self.K, self.peer.stats_ptrs[par], self.peer.world,
-                                                     _ptr(self.train.deg), _ptr(self.theta), _ptr(self.p),
-                                                     self._stream()), "tip_normalise_peers")
-            self.launches += 2
+            self._peer_mstep(par)
             return
         self.em_step_host_rows(h_rows, compact)
         if self.world > 1:
             _dist.allreduce_sum_(self.stats, self.group)
         self.normalise()
 
+    @_on_device
     def normalise(self):
         _cabi.check(self.lib.tip_normalise(self.P, self.K, _ptr(self.stats), _ptr(self.train.deg), _ptr(self.theta),
                                            _ptr(self.p), self._stream()), "tip_normalise")
         self.launches += 1
 
-    def em_iteration(self):
-        """One make_iteration: E-step, sum of statistics over link shards, M-step."""
+    @_on_device
+    def _iteration_body(self, par):
+        """E-step, sum of statistics over link shards, M-step, on statistics buffer `par` of the peer exchange."""
         if self.peer is not None:
-            par = self._iter & 1
-            self._iter += 1
             self.em_step(self.peer.stats(par))
-            _cabi.check(self.lib.tip_peer_barrier(self.peer.flag_ptrs, _ptr(self.peer.epoch), self.peer.rank,
-                                                  self.peer.world, self._stream()), "tip_peer_barrier")
-            _cabi.check(self.lib.tip_normalise_peers(self.P, self.K, self.peer.stats_ptrs[par], self.peer.world,
-                                                     _ptr(self.train.deg), _ptr(self.theta), _ptr(self.p),
-                                                     self._stream()), "tip_normalise_peers")
-            self.launches += 2
+            self._peer_mstep(par)
             return
         self.em_step()
         if self.world > 1:
             _dist.allreduce_sum_(self.stats, self.group)
         self.normalise()
 
+    def em_iteration(self):
+        """One make_iteration.  The peer exchange double-buffers the statistics: iteration i uses buffer i & 1, and
+        `_iter` is the ONE counter eager iterations and graph replays both advance, so the two can be mixed."""
+        self._iteration_body(self._iter & 1)
+        self._iter += 1
+
     # ---- CUDA-graph replay of whole iterations (two graphs when the statistics are double-buffered) ----
+    @_on_device
     def capture_graphs(self):
         with torch.cuda.device(self.device):
             self.em_iteration()                           # warm-up outside capture (function attributes, NCCL)
             torch.cuda.synchronize(self.device)
             self._graphs, self._graph_launches = [], 0
-            for _ in range(2 if self.peer is not None else 1):
+            for par in range(2 if self.peer is not None else 1):      # graph `par` works on statistics buffer `par`
                 g = torch.cuda.CUDAGraph()
                 before = self.launches
                 with torch.cuda.graph(g):
-                    self.em_iteration()
+                    self._iteration_body(par)
                 self._graph_launches = self.launches - before
                 self.launches = before
                 self._graphs.append(g)
-            self._gpos = 0
             self._graph_key = (self.train.rows.data_ptr(), self.train.n_rows, self.flags)
 
+    @_on_device
     def graph_step(self):
-        self._graphs[self._gpos % len(self._graphs)].replay()
-        self._gpos += 1
+        self._graphs[self._iter % len(self._graphs)].replay()
+        self._iter += 1
         self.launches += self._graph_launches
 
     def em_iterations(self, n: int, use_graph: bool = True):
@@ -284,6 +340,7 @@ class EMEngine:
             self.graph_step()
 
     # ------------------------------------------------------------------ likelihood / scoring / metrics
+    @_on_device
     def loglik(self, which: str = "train") -> float:
         links = self.train if which == "train" else self.test
         if links is None:
@@ -295,8 +352,11 @@ class EMEngine:
         self.launches += 2 if (self.K <= 10 and not (self.flags & _cabi.TIP_EM_FORCE_GENERIC)) else 1
         if self.world > 1 and which == "train":
             _dist.allreduce_sum_(self.ll_out, self.group)
-        return float(self.ll_out.item())
+        value = float(self.ll_out.item())
+        self._check_peer()
+        return value
 
+    @_on_device
     def step_loglik(self) -> float:
         """log-likelihood by-product of the last E-step of THIS rank's rows (of the parameters that step started
         from); needs TIP_EM_WITH_LOGLIK on the K-specialised path."""
@@ -304,6 +364,7 @@ class EMEngine:
             return float(self.peer.stats((self._iter - 1) & 1)[-1].item())
         return float(self.stats[-1].item())
 
+    @_on_device
     def scores(self) -> torch.Tensor:
         g1, g2, g3, _ = self.test_ids
         T = int(g1.numel())
@@ -313,6 +374,21 @@ class EMEngine:
         self.launches += 1
         return out
 
+    @_on_device
+    def sort_scores(self, scores: torch.Tensor):
+        """tip_sort_scores: (test-set index, score) in descending score order as numpy arrays."""
+        T = int(scores.numel())
+        nb = ctypes.c_size_t(0)
+        _cabi.check(self.lib.tip_sort_scores_workspace_bytes(T, ctypes.byref(nb)), "tip_sort_scores_workspace_bytes")
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=self.device)
+        order = torch.empty(T, dtype=torch.int32, device=self.device)
+        out = torch.empty(T, dtype=torch.float64, device=self.device)
+        _cabi.check(self.lib.tip_sort_scores(_ptr(scores), T, _ptr(ws), nb.value, _ptr(order), _ptr(out), self._stream()),
+                    "tip_sort_scores")
+        self.launches += 2
+        return order.cpu().numpy(), out.cpu().numpy()
+
+    @_on_device
     def metric_counts(self, scores: torch.Tensor, positives_number: int) -> dict:
         """Integer ingredients of calculate_metrics (TIP.py:583-637); ratios are formed by the caller."""
         labels = self.test_ids[3]
