@@ -665,10 +665,10 @@ def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
     d2h = th_h.numel() * 8 + p_h.numel() * 8
     steps = args.steps
 
-    def make_step(compact, streamed=True):
+    def make_step(compact, streamed=True, em_flags=0):
         if world == 1:
             src = rows8_h if compact else rows_h
-            fl = _cabi.TIP_ROWS_COMPACT8 if compact else 0
+            fl = (_cabi.TIP_ROWS_COMPACT8 if compact else 0) | em_flags
 
             def step():
                 rc = lib.tip_em_iterations_host(P, K, src.data_ptr(), n_rows, eng.train.n_rows_r0,
@@ -745,10 +745,24 @@ def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
         th_h.copy_(torch.from_numpy(np.ascontiguousarray(theta0)))
         p_h.copy_(torch.from_numpy(np.ascontiguousarray(pr0)))
         dt16, dt, _ = run_both(False)
+    alt = None
     if world == 1:
-        api = ("tip_em_iterations_host (C ABI, pinned host buffers, 8-byte rows: TIP_ROWS_COMPACT8); one iteration per call, so "
-               "the K^3-per-link kernel that follows the rows' DMA front runs it (the slot-segmented kernels need the rows in "
-               "three orders, i.e. all of them on the device first)")
+        # the same call with the slot-segmented kernels: rows land, pass A runs while the copy stream sorts them into orders
+        # b and c, then passes B + C.  The K^3-per-link kernel can follow the rows' DMA front but scatters with atomics (slow
+        # on hub-shaped links); the faster of the two is the headline, the other is listed
+        seg_flags = eng.flags & (_cabi.TIP_EM_SLOT_SEGMENTED | _cabi.TIP_EM_GATHER_L1)
+        if seg_flags:
+            th_h.copy_(torch.from_numpy(np.ascontiguousarray(theta0)))
+            p_h.copy_(torch.from_numpy(np.ascontiguousarray(pr0)))
+            dts = timed(make_step(True, True, seg_flags))
+            alt = {"slot_segmented_after_landing": {"value": L_total * steps / dts, "ms_per_step": 1e3 * dts / steps},
+                   "k3_following_the_dma_front": {"value": L_total * steps / dt, "ms_per_step": 1e3 * dt / steps, "streamed": streamed}}
+            if dts < dt:
+                dt = dts
+        api = ("tip_em_iterations_host (C ABI, pinned host buffers, 8-byte rows: TIP_ROWS_COMPACT8), one iteration per call; "
+               + ("slot-segmented kernels: the rows land, pass A runs while a second stream sorts them into the orders of slots b "
+                  "and c, then passes B + C" if alt and dt == dts else
+                  "the K^3-per-link kernel follows the rows' DMA front"))
     else:
         api = ("EMEngine.em_iteration_host_rows: pinned host buffers, 8-byte rows, tip_em_step_host_rows follows the DMA "
                "front (link-sharded, %s exchange)" % args.exchange)
@@ -757,7 +771,7 @@ def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
     # bytes are whole-job like `value`: every rank copies its own shard's rows plus the replicated parameters
     return {"value": L_total * steps / dt, "unit": UNIT, "streamed": streamed,
             "h2d_bytes_per_step": int(n_rows * 8 + fixed) * world, "d2h_bytes_per_step": int(d2h) * world,
-            "bytes_are": "summed over the %d rank(s)" % world, "ms_per_step": 1e3 * dt / steps, "api": api,
+            "bytes_are": "summed over the %d rank(s)" % world, "ms_per_step": 1e3 * dt / steps, "api": api, "variants": alt,
             "rows16": {"value": L_total * steps / dt16, "ms_per_step": 1e3 * dt16 / steps,
                        "h2d_bytes_per_step": int(n_rows * 16 + fixed) * world}}
 

@@ -122,8 +122,11 @@ int tip_em_step(int P, int K, const void *d_rows, int64_t n_rows, int64_t n_rows
  * sentinel and queues ONE host-to-device copy on `copy_stream`; the fused kernel, launched on `stream`, polls the
  * rows of each tile until they have landed, so the E-step follows the DMA front instead of waiting for the copy
  * (one launch, no chunking).  Queue small parameter copies BEFORE this call: the host-to-device engine serves all
- * streams in submission order.  d_err: 4 bytes of device memory, zero on entry; set to 1 when a tile waited more
- * than 5 s (the statistics are then incomplete).  Plain fp64 kernels for K <= 10 only (-1 otherwise: copy the rows
+ * streams in submission order.  d_err: 256 bytes of device memory, zero on entry; word 0 is set to 1 when a tile waited
+ * more than 5 s (the statistics are then incomplete) and to 2 when the words the kernel consumed do not add up to the
+ * words that finally landed (checked by a verification kernel once the copy is complete: a kernel racing a DMA has no
+ * memory-model guarantee of seeing whole words, so the race is PROVEN harmless per call) - in both cases discard the
+ * statistics and call tip_em_step on d_rows_dev, which then holds the rows.  Plain fp64 kernels for K <= 10 only (-1 otherwise: copy the rows
  * and call tip_em_step).  `stream` and `copy_stream` must differ.  Not capturable in a CUDA graph. */
 int tip_em_step_host_rows(int P, int K, const void *h_rows, int64_t n_rows, int64_t n_rows_r0, unsigned row_flags,
                           void *d_rows_dev, const double *d_theta, const double *d_p, double *d_stats, void *d_ws,
@@ -185,8 +188,12 @@ int tip_reduce_samples(int S, int64_t T, const double *d_scores, const int32_t *
  * Plain fp64, K <= 10: the first iteration is STREAMED - one copy of all rows on a side stream, the E-step kernel
  * polls each tile's rows until they have landed and so follows the DMA front (see tip_em_step_host_rows).  If the
  * rows do not arrive within 5 s (a platform that cannot run the copy beside the kernel) the call returns -3 and
- * h_theta / h_p are undefined; the environment variable TIP_HOST_NO_STREAM=1 (read on every call) selects the
- * copy-in-chunks-then-compute path instead.  One call at a time per process (the scratch is shared). */
+ * h_theta / h_p are undefined; if the words the kernel consumed do not add up to the words that landed (verified on the
+ * device after the copy) no M-step of the call takes effect and all iterations are repeated from the resident rows
+ * before the call returns - the result is then still exact, only slower; the environment variable TIP_HOST_NO_STREAM=1 (read on every call) selects the
+ * copy-in-chunks-then-compute path instead.  With TIP_EM_SLOT_SEGMENTED in `flags` the rows are ordered on the device
+ * (tip_order_rows) once they have landed and iterations 2..n_iter run the slot-segmented kernels.
+ * One call at a time per process (the scratch is shared). */
 int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t n_rows, int64_t n_rows_r0,
                            const int32_t *h_deg, double *h_theta, double *h_p, int n_iter, unsigned flags);
 

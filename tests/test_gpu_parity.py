@@ -799,3 +799,76 @@ def test_streamed_host_entry_gives_up_cleanly(torch_cuda, monkeypatch):
                                     th_h.ctypes.data, p_h.ctypes.data, 1, 0)                # streamed again, healthy
     assert rc == 0, lib.tip_last_error()
     assert _relerr(th_h, th_a) < 1e-11 and _relerr(p_h, p_a) < 1e-11
+
+
+def test_streamed_host_rows_many_sizes_and_repeats(torch_cuda):
+    """The streamed E-step races a kernel against the rows' DMA: it must give the resident-row statistics
+    every time - sizes from a few tiles to 1.6 M rows, both row formats, pinned rows, repeated back to back - and the
+    verification of what it consumed must never fire on a healthy platform."""
+    torch = torch_cuda
+    from trigenicinteractionpredictor_b200 import _cabi
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    lib = _cabi.load()
+    P, K = 700, 10
+    for L, reps in ((300, 4), (5000, 4), (120_000, 6), (1_600_000, 6)):
+        g, n0, n1, theta, pr = _random_problem(P, L, K, 1000 + L % 97)
+        eng = EMEngine(P, K, flags=0)
+        eng.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+        eng.set_params(theta, pr)
+        eng.em_step()
+        want = eng.stats.cpu().numpy().copy()
+        rows16 = eng.train.rows.cpu().pin_memory()
+        rows8 = torch.empty(eng.train.n_rows, dtype=torch.int64).pin_memory()
+        assert lib.tip_rows_compact_host(rows16.data_ptr(), eng.train.n_rows, rows8.data_ptr()) == 0
+        for rep in range(reps):
+            for compact, src in ((False, rows16), (True, rows8)):
+                eng.em_step_host_rows(src, compact)
+                got = eng.stats.cpu().numpy()
+                assert eng.host_rows_arrived(), "L=%d rep %d: the streamed step reported a stall or a checksum mismatch" % (L, rep)
+                assert _relerr(got[: P * K], want[: P * K]) < 1e-12 and _relerr(got[P * K:-1], want[P * K:-1]) < 1e-12
+
+
+def test_streamed_step_checksum_mismatch_is_detected_and_repaired(torch_cuda, monkeypatch):
+    """TIP_STREAM_INJECT_FAULT makes the verification disagree with what the kernel consumed: tip_em_iterations_host
+    must still return the exact iteration (M-steps held back, iterations repeated from the resident rows) and
+    tip_em_step_host_rows must flag the statistics (host_rows_arrived() False)."""
+    torch = torch_cuda
+    from trigenicinteractionpredictor_b200 import _cabi
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    lib = _cabi.load()
+    P, L, K = 400, 60000, 10
+    g, n0, n1, theta, pr = _random_problem(P, L, K, 17)
+    a = EMEngine(P, K, flags=0)
+    a.set_train_links(g[:, 0], g[:, 1], g[:, 2], n0, n1)
+    a.set_params(theta, pr)
+    for _ in range(3):
+        a.em_iteration()
+    th_a, p_a = a.get_params()
+    rows = a.train.rows.cpu().pin_memory()
+    deg = np.ascontiguousarray(a.degrees().astype(np.int32))
+    monkeypatch.setenv("TIP_STREAM_INJECT_FAULT", "1")
+    monkeypatch.setenv("TIP_HOST_SEG3_AFTER_STREAM", "1")    # flags 32: streamed K^3 first iteration, then the rows are ordered
+    for n_iter_flags in ((3, 0), (3, 32)):
+        th_h, p_h = np.ascontiguousarray(theta.copy()), np.ascontiguousarray(pr.copy())
+        rc = lib.tip_em_iterations_host(P, K, rows.data_ptr(), a.train.n_rows, a.train.n_rows_r0, deg.ctypes.data,
+                                        th_h.ctypes.data, p_h.ctypes.data, n_iter_flags[0], n_iter_flags[1])
+        assert rc == 0, lib.tip_last_error()
+        assert _relerr(th_h, th_a) < 1e-10 and _relerr(p_h, p_a) < 1e-10
+    a.set_params(theta, pr)
+    a.em_step_host_rows(rows, False)
+    assert not a.host_rows_arrived()
+    monkeypatch.delenv("TIP_STREAM_INJECT_FAULT")
+    monkeypatch.delenv("TIP_HOST_SEG3_AFTER_STREAM")
+    a.em_step_host_rows(rows, False)
+    assert a.host_rows_arrived()
+    # and without the fault: the slot-segmented kernels behind the host entry (rows ordered on the device while pass A runs),
+    # 16-byte and 8-byte host rows, repeated (the scratch and the events are reused)
+    rows8 = torch.empty(a.train.n_rows, dtype=torch.int64).pin_memory()
+    assert lib.tip_rows_compact_host(rows.data_ptr(), a.train.n_rows, rows8.data_ptr()) == 0
+    for rep in range(3):
+        for src, fl in ((rows, 32), (rows8, 32 | 16), (rows8, 32 | 64 | 16)):
+            th_h, p_h = np.ascontiguousarray(theta.copy()), np.ascontiguousarray(pr.copy())
+            rc = lib.tip_em_iterations_host(P, K, src.data_ptr(), a.train.n_rows, a.train.n_rows_r0, deg.ctypes.data,
+                                            th_h.ctypes.data, p_h.ctypes.data, 3, fl)
+            assert rc == 0, lib.tip_last_error()
+            assert _relerr(th_h, th_a) < 1e-10 and _relerr(p_h, p_a) < 1e-10

@@ -129,6 +129,29 @@ def test_shard_bounds_and_sample_assignment():
     assert sorted(s for r in range(8) for s in tdist.samples_for_rank(10, 50, r, 8)) == list(range(10, 60))
 
 
+@pytest.mark.parametrize("K", [1, 2, 3, 10, 17, 32])
+def test_block_drawn_initialisation_equals_the_reference_loops(K):
+    """initialize_parameters draws all P*K + 2K^3 numbers in one block (numpy RandomState on the random module's MT19937
+    state) and restates builtin sum(): values, and the position of the `random` stream afterwards, must be bit-identical
+    to one random.random() per cell in the reference's order (TIP.py:117-170)."""
+    import random
+    from trigenicinteractionpredictor_b200.TrigenicInteractionPredictor import Model
+    m = Model()
+    m.P = 613
+    random.seed(4242 + K)
+    th1, p1 = m._draw_parameters_loops(K, 2)
+    after_loops, next_loops = random.getstate(), random.random()
+    random.seed(4242 + K)
+    th2, p2 = m._draw_parameters_fast(K, 2)
+    assert th2 is not None
+    after_fast, next_fast = random.getstate(), random.random()
+    assert th2.tolist() == th1 and p2.tolist() == p1
+    assert after_fast == after_loops and next_fast == next_loops
+    random.seed(4242 + K)
+    m.initialize_parameters(K)
+    assert m.theta == th1 and m.pr == p1 and isinstance(m.theta, list) and isinstance(m.pr[0][0][0], list)
+
+
 def test_vectorised_soa_equals_the_per_link_loop():
     """Model._soa parses all keys in one pass; it must give what splitting every key in a Python loop gives."""
     from trigenicinteractionpredictor_b200.TrigenicInteractionPredictor import Model

@@ -17,6 +17,7 @@ names = subprocess.run(["c++filt"] + [r[1] for r in rows], capture_output=True, 
 print("%-12s %5s %7s %7s  kernel" % ("object", "regs", "spill_st", "spill_ld"))
 for (obj, _, regs, st, ld), name in zip(rows, names):
     name = re.sub(r"\(.*", "", name)
-    if st or ld or "seg3" in name or "em_fused" in name or "finalize" in name:
+    # every kernel that spills, and the K = 10 / 16 / 32 instances of the E-step families
+    if st or ld or re.search(r"(seg3_pass_kernel|seg3_finish_kernel|em_fused_kernel|em_finalize_kernel|loglik_\w+)<(10|16|32)[,>]", name):
         print("%-12s %5d %7d %7d  %s" % (obj, regs, st, ld, name[:110]))
-print("\n%d kernels in total; kernels without spills outside the E-step families are not listed" % len(rows))
+print("\n%d kernels in total; listed: every kernel with spills, and the K = 10 / 16 / 32 instances of the E-step families" % len(rows))

@@ -125,6 +125,8 @@ class Model:
     def theta(self):
         self._pull()
         self._exposed = True
+        if isinstance(self._theta_host, np.ndarray):
+            self._theta_host = self._theta_host.tolist()
         return self._theta_host
 
     @theta.setter
@@ -137,6 +139,8 @@ class Model:
     def pr(self):
         self._pull()
         self._exposed = True
+        if isinstance(self._pr_host, np.ndarray):
+            self._pr_host = self._pr_host.tolist()
         return self._pr_host
 
     @pr.setter
@@ -181,7 +185,16 @@ class Model:
         except ValueError:
             self.K = 10
         self.vlikelihood = []
-        K, R, rnd = self.K, self.R, random.random
+        K, R = self.K, self.R
+        theta, pr = self._draw_parameters_fast(K, R)
+        if theta is None:
+            theta, pr = self._draw_parameters_loops(K, R)
+        self._theta_host, self._pr_host = theta, pr
+        self._params_on, self._host_valid, self._exposed = "host", True, False
+
+    def _draw_parameters_loops(self, K, R):
+        """The reference's loops, one random.random() per cell (TIP.py:117-170)."""
+        rnd = random.random
         # draw order: all theta rows, then p cells in (i, j, k, r) order (TIP.py:117-139)
         theta = [[rnd() for _ in range(K)] for _ in range(self.P)]
         pr = [[[[rnd() for _ in range(R)] for _ in range(K)] for _ in range(K)] for _ in range(K)]
@@ -209,8 +222,43 @@ class Model:
                             cell[r] /= acc
                         except ZeroDivisionError:
                             cell[r] /= (acc + self.eps)
-        self._theta_host, self._pr_host = theta, pr
-        self._params_on, self._host_valid, self._exposed = "host", True, False
+        return theta, pr
+
+    def _draw_parameters_fast(self, K, R):
+        """The same numbers without a Python call per draw: `random.random()` is MT19937's 53-bit output, exactly what
+        numpy's legacy RandomState.random_sample produces from the same state, so the whole block of P*K + K^3*R draws
+        is taken from a RandomState seeded with the `random` module's state, and that module's state is then moved to
+        where the loops would have left it (consecutive samples continue one stream, TIP.py:1149).  Row totals are the
+        builtin sum() of TIP.py:151 restated (compensated since Python 3.12, so not numpy's pairwise sum); divisions are
+        elementwise IEEE either way.  Returns arrays (the list mirrors are made when a caller reads theta / pr), or
+        (None, None) in the cases the loops treat specially (a row summing to < eps is redrawn, a zero total divides by
+        total + eps): the caller then runs the loops from the untouched state.  tests/test_host_model.py holds the two
+        paths bit-identical, RNG position included."""
+        state = random.getstate()
+        if state[0] != 3 or R != 2:
+            return None, None
+        rs = np.random.RandomState()
+        rs.set_state(("MT19937", np.array(state[1][:-1], dtype=np.uint32), state[1][-1], 0, 0.0))
+        th = rs.random_sample(self.P * K).reshape(self.P, K)
+        pp = rs.random_sample(K * K * K * R).reshape(K, K, K, R)
+        # builtin sum() over a row, as CPython >= 3.12 computes it (Neumaier-compensated), all rows at once
+        f = np.zeros(self.P)
+        c = np.zeros(self.P)
+        for k in range(K):
+            x = th[:, k]
+            t = f + x
+            c += np.where(np.abs(f) >= np.abs(x), (f - t) + x, (x - t) + f)
+            f = t
+        totals = f + c if sys.version_info >= (3, 12) else None
+        if totals is None:
+            totals = np.array([sum(row) for row in th.tolist()], dtype=np.float64)
+        cell_tot = (0.0 + pp[..., 0]) + pp[..., 1]
+        # the loops redraw a row whose sequential sum is < eps and divide by total + eps when a total is zero
+        if float(totals.min()) < 1e-6 or (cell_tot == 0.0).any():
+            return None, None
+        ns = rs.get_state()
+        random.setstate((3, tuple(int(x) for x in ns[1]) + (int(ns[2]),), state[2]))
+        return th / totals[:, None], pp / cell_tot[..., None]
 
     # ------------------------------------------------------------------------------------------
     # link digestion

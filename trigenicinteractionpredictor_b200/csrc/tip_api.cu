@@ -109,10 +109,11 @@ extern "C" int tip_em_step_host_rows(int P, int K, const void *h_rows, int64_t n
     const size_t need = em_tuned_workspace_bytes(P, K, false);
     TIP_REQUIRE(need == 0 || (d_ws != nullptr && ws_bytes >= need),
                 "tip_em_step_host_rows: K=%d needs %zu bytes of workspace (got %zu), see tip_em_workspace_bytes", K, need, ws_bytes);
-    static cudaEvent_t ev_free = nullptr, ev_filled = nullptr;
+    static cudaEvent_t ev_free = nullptr, ev_filled = nullptr, ev_done = nullptr;
     if (!ev_free) {
         TIP_CHECK_CUDA(cudaEventCreateWithFlags(&ev_free, cudaEventDisableTiming));
         TIP_CHECK_CUDA(cudaEventCreateWithFlags(&ev_filled, cudaEventDisableTiming));
+        TIP_CHECK_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
     }
     const bool compact = (row_flags & TIP_ROWS_COMPACT8) != 0;
     const size_t bytes = (size_t)n_rows * (compact ? 8 : 16);
@@ -123,17 +124,23 @@ extern "C" int tip_em_step_host_rows(int P, int K, const void *h_rows, int64_t n
     TIP_CHECK_CUDA(cudaMemsetAsync(d_rows_dev, 0xFF, bytes, cs));
     TIP_CHECK_CUDA(cudaEventRecord(ev_filled, cs));
     TIP_CHECK_CUDA(cudaMemcpyAsync(d_rows_dev, h_rows, bytes, cudaMemcpyHostToDevice, cs));
+    TIP_CHECK_CUDA(cudaEventRecord(ev_done, cs));
     TIP_CHECK_CUDA(cudaMemsetAsync(d_stats, 0, sizeof(double) * (size_t)tip_stats_len(P, K), st));
     bool handled = false;
     int rc = launch_em_tuned(P, K, nullptr, 0, 0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws), false, false, false,
                              st, &handled, 1);
     if (rc) return rc;
     TIP_CHECK_CUDA(cudaStreamWaitEvent(st, ev_filled, 0));
-    rc = launch_em_streamed(P, K, d_rows_dev, n_rows, n_rows_r0, d_theta, d_stats, reinterpret_cast<double *>(d_ws), d_err,
+    unsigned long long *chk = reinterpret_cast<unsigned long long *>(d_err) + 4;   // bytes 32..63 of the error block
+    rc = launch_em_streamed(P, K, d_rows_dev, n_rows, n_rows_r0, d_theta, d_stats, reinterpret_cast<double *>(d_ws), d_err, chk,
                             compact, st);
     if (rc) return rc;
-    return launch_em_tuned(P, K, nullptr, 0, 0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws), false, false, false, st,
-                           &handled, 4);
+    rc = launch_em_tuned(P, K, nullptr, 0, 0, d_theta, d_p, d_stats, reinterpret_cast<double *>(d_ws), false, false, false, st,
+                         &handled, 4);
+    if (rc) return rc;
+    // the copy is complete: what the kernel consumed must be what landed (d_err[0] = 2 otherwise)
+    TIP_CHECK_CUDA(cudaStreamWaitEvent(st, ev_done, 0));
+    return launch_stream_verify(d_rows_dev, n_rows, compact, chk, d_err, st);
 }
 
 extern "C" int tip_normalise(int P, int K, const double *d_stats, const int32_t *d_deg, double *d_theta, double *d_p,
@@ -180,6 +187,10 @@ struct HostPool {
     cudaEvent_t ev[kHostChunks] = {};
     // streamed first iteration: error word on the device and its read-back in pinned host memory
     unsigned *err = nullptr, *h_err = nullptr;
+    unsigned long long *chk = nullptr;   // device: checksums of the streamed step and its "do not trust" flag
+    void *order_ws = nullptr, *order_ws2 = nullptr;
+    size_t order_ws_b = 0, order_ws2_b = 0;
+    cudaEvent_t ev_rows = nullptr, ev_ordered = nullptr;
 };
 HostPool g_pool;
 
@@ -257,6 +268,10 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
         TIP_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&g.h_err), 256, cudaHostAllocMapped));
         memset(g.h_err, 0, 256);
         TIP_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&g.err), g.h_err, 0));
+        TIP_CHECK_CUDA(cudaEventCreateWithFlags(&g.ev_rows, cudaEventDisableTiming));
+        TIP_CHECK_CUDA(cudaEventCreateWithFlags(&g.ev_ordered, cudaEventDisableTiming));
+        TIP_CHECK_CUDA(cudaMalloc(reinterpret_cast<void **>(&g.chk), 256));
+        TIP_CHECK_CUDA(cudaMemset(g.chk, 0, 256));
     }
     const size_t nth = (size_t)P * K * 8, np = (size_t)2 * K * K * K * 8, nst = (size_t)tip_stats_len(P, K) * 8;
     size_t wsb = 0;
@@ -266,11 +281,45 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
     flags &= ~TIP_ROWS_COMPACT8;
     const size_t row_b = compact ? 8 : 16;  // bytes per row in the HOST buffer
     if (compact && (rc = ensure(&g.rows8, &g.rows8_b, (size_t)n_rows * 8))) return rc;
-    if ((rc = ensure(&g.rows, &g.rows_b, (size_t)n_rows * 16)) || (rc = ensure(&g.theta, &g.theta_b, nth)) ||
+    // slot-segmented iterations need the rows in three orders plus the tile schedules: ordered on the device once the
+    // rows have landed (the first, streamed iteration runs the K^3-per-link kernel, which needs order a only)
+    const bool seg3 = seg3_flag(flags);
+    size_t order_b = 0;
+    if (seg3 && tip_order_rows_workspace_bytes(n_rows, &order_b) != 0) return -1;
+    if (seg3 && ((rc = ensure(&g.order_ws, &g.order_ws_b, order_b)) || (rc = ensure(&g.order_ws2, &g.order_ws2_b, order_b)))) return rc;
+    if ((rc = ensure(&g.rows, &g.rows_b, (size_t)n_rows * 16 + (seg3 ? (size_t)tip_order_rows_out_bytes(n_rows) : 0))) || (rc = ensure(&g.theta, &g.theta_b, nth)) ||
         (rc = ensure(&g.p, &g.p_b, np)) || (rc = ensure(&g.stats, &g.stats_b, nst)) ||
         (rc = ensure(&g.deg, &g.deg_b, (size_t)P * 4)) || (rc = ensure(&g.ws, &g.ws_b, wsb)))
         return rc;
-    const bool tuned = uses_tuned(K, flags);
+    if (seg3 && n_iter > 0 && n_rows >= 32 && getenv("TIP_HOST_SEG3_AFTER_STREAM") == nullptr) {
+        // Slot-segmented kernels for EVERY iteration.  The rows land first (they are needed in three orders, so nothing
+        // can follow the DMA front); then pass A of the first iteration runs on the main stream while the copy stream
+        // sorts the rows into orders b and c, which only passes B and C need.
+        TIP_CHECK_CUDA(cudaMemcpyAsync(g.theta, h_theta, nth, cudaMemcpyHostToDevice, g.st));
+        TIP_CHECK_CUDA(cudaMemcpyAsync(g.p, h_p, np, cudaMemcpyHostToDevice, g.st));
+        TIP_CHECK_CUDA(cudaMemcpyAsync(compact ? g.rows8 : g.rows, h_rows, (size_t)n_rows * row_b, cudaMemcpyHostToDevice, g.st));
+        if (compact && (rc = launch_rows_expand(g.rows8, g.rows, n_rows, g.st))) return rc;
+        TIP_CHECK_CUDA(cudaEventRecord(g.ev_rows, g.st));
+        TIP_CHECK_CUDA(cudaMemcpyAsync(g.deg, h_deg, (size_t)P * 4, cudaMemcpyHostToDevice, g.st));
+        char *rows_bc = (char *)g.rows + (size_t)n_rows * 16;
+        TIP_CHECK_CUDA(cudaStreamWaitEvent(g.copy, g.ev_rows, 0));
+        if ((rc = order_rows_parts(g.rows, n_rows, n_rows_r0, g.order_ws2, g.order_ws2_b, rows_bc, g.copy, 2))) return rc;
+        TIP_CHECK_CUDA(cudaEventRecord(g.ev_ordered, g.copy));
+        if ((rc = order_rows_parts(g.rows, n_rows, n_rows_r0, g.order_ws, g.order_ws_b, rows_bc, g.st, 1))) return rc;
+        for (int it = 0; it < n_iter; ++it) {
+            if (it == 0) seg3_wait_before_bc(g.ev_ordered);
+            rc = tip_em_step(P, K, g.rows, n_rows, n_rows_r0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
+                             g.ws, g.ws_b, flags, g.st);
+            if (rc) return rc;
+            rc = launch_normalise(P, K, (const double *)g.stats, (const int32_t *)g.deg, (double *)g.theta, (double *)g.p, g.st);
+            if (rc) return rc;
+        }
+        TIP_CHECK_CUDA(cudaMemcpyAsync(h_theta, g.theta, nth, cudaMemcpyDeviceToHost, g.st));
+        TIP_CHECK_CUDA(cudaMemcpyAsync(h_p, g.p, np, cudaMemcpyDeviceToHost, g.st));
+        TIP_CHECK_CUDA(cudaStreamSynchronize(g.st));
+        return 0;
+    }
+    const bool tuned = uses_tuned(K, flags & ~(TIP_EM_SLOT_SEGMENTED | TIP_EM_GATHER_L1));
     const bool streamed = tuned && n_iter > 0 && n_rows >= 32 * kHostChunks &&
                           em_streamed_available(K, (flags & TIP_EM_WITH_LOGLIK) != 0, (flags & TIP_EM_FP32_COMPUTE) != 0,
                                                 seg_flag(flags)) && getenv("TIP_HOST_NO_STREAM") == nullptr;
@@ -299,13 +348,18 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
         if (rc) return rc;
         TIP_CHECK_CUDA(cudaStreamWaitEvent(g.st, g.ev[0], 0));
         rc = launch_em_streamed(P, K, s_dst, n_rows, n_rows_r0, (const double *)g.theta, (double *)g.stats, (double *)g.ws,
-                                g.err, compact, g.st);
+                                g.err, g.chk, compact, g.st);
         if (rc) return rc;
         rc = launch_em_tuned(P, K, nullptr, 0, 0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
                              (double *)g.ws, false, false, false, g.st, &handled, 4);
         if (rc) return rc;
         TIP_CHECK_CUDA(cudaStreamWaitEvent(g.st, g.ev[1], 0));
-        rc = tip_normalise(P, K, (const double *)g.stats, (const int32_t *)g.deg, (double *)g.theta, (double *)g.p, g.st);
+        // the copy is complete: check that the kernel consumed exactly what landed; if not, the flag g.chk[3] makes every
+        // M-step of this call a no-op (theta / p stay as uploaded) and the iterations are repeated below from resident rows
+        rc = launch_stream_verify(s_dst, n_rows, compact, g.chk, g.err, g.st);
+        if (rc) return rc;
+        rc = launch_normalise(P, K, (const double *)g.stats, (const int32_t *)g.deg, (double *)g.theta, (double *)g.p, g.st,
+                              g.chk + 3);
         if (rc) return rc;
         if (compact && n_iter > 1 && (rc = launch_rows_expand(g.rows8, g.rows, n_rows, g.st))) return rc;
         it0 = 1;
@@ -347,16 +401,34 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
         TIP_CHECK_CUDA(cudaMemcpyAsync(compact ? g.rows8 : g.rows, h_rows, (size_t)n_rows * row_b, cudaMemcpyHostToDevice, g.st));
         if (compact && (rc = launch_rows_expand(g.rows8, g.rows, n_rows, g.st))) return rc;
     }
-    for (int it = it0; it < n_iter; ++it) {
-        rc = tip_em_step(P, K, g.rows, n_rows, n_rows_r0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
-                         g.ws, g.ws_b, flags, g.st);
-        if (rc) return rc;
-        rc = tip_normalise(P, K, (const double *)g.stats, (const int32_t *)g.deg, (double *)g.theta, (double *)g.p, g.st);
-        if (rc) return rc;
+    auto run_resident = [&](int first) -> int {
+        if (seg3 && first < n_iter) {
+            int rc2 = tip_order_rows(g.rows, n_rows, n_rows_r0, g.order_ws, g.order_ws_b, (char *)g.rows + (size_t)n_rows * 16, g.st);
+            if (rc2) return rc2;
+        }
+        for (int it = first; it < n_iter; ++it) {
+            int rc2 = tip_em_step(P, K, g.rows, n_rows, n_rows_r0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
+                                  g.ws, g.ws_b, flags, g.st);
+            if (rc2) return rc2;
+            rc2 = launch_normalise(P, K, (const double *)g.stats, (const int32_t *)g.deg, (double *)g.theta, (double *)g.p, g.st,
+                                   streamed ? g.chk + 3 : nullptr);
+            if (rc2) return rc2;
+        }
+        TIP_CHECK_CUDA(cudaMemcpyAsync(h_theta, g.theta, nth, cudaMemcpyDeviceToHost, g.st));
+        TIP_CHECK_CUDA(cudaMemcpyAsync(h_p, g.p, np, cudaMemcpyDeviceToHost, g.st));
+        TIP_CHECK_CUDA(cudaStreamSynchronize(g.st));
+        return 0;
+    };
+    if ((rc = run_resident(it0))) return rc;
+    if (streamed && g.h_err[0] == 2u) {
+        // the streamed kernel consumed a word that was not what finally landed: nothing was normalised (theta / p on the
+        // device are still the uploaded ones) - repeat every iteration from the rows that are now resident
+        g.h_err[0] = 0;
+        TIP_CHECK_CUDA(cudaMemsetAsync(g.chk, 0, 32, g.st));
+        if (compact && n_iter <= 1 && (rc = launch_rows_expand(g.rows8, g.rows, n_rows, g.st))) return rc;
+        if (getenv("TIP_HOST_STREAM_DEBUG")) fprintf(stderr, "stream dbg: checksum mismatch, iterations repeated from resident rows\n");
+        if ((rc = run_resident(0))) return rc;
     }
-    TIP_CHECK_CUDA(cudaMemcpyAsync(h_theta, g.theta, nth, cudaMemcpyDeviceToHost, g.st));
-    TIP_CHECK_CUDA(cudaMemcpyAsync(h_p, g.p, np, cudaMemcpyDeviceToHost, g.st));
-    TIP_CHECK_CUDA(cudaStreamSynchronize(g.st));
     if (streamed && getenv("TIP_HOST_STREAM_DEBUG")) {
         unsigned long long d[5];
         memcpy(d, reinterpret_cast<unsigned long long *>(g.h_err) + 8, sizeof(d));

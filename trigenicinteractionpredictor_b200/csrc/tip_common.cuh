@@ -90,9 +90,14 @@ size_t em_tuned_workspace_bytes(int P, int K, bool seg);
 int launch_em_seg3(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
                    double *stats, double *ws, bool gather_l1, cudaStream_t st);
 size_t em_seg3_workspace_bytes(int P, int K, int64_t n_rows);
+int order_rows_parts(const void *d_rows, int64_t n_rows, int64_t n_rows_r0, void *d_ws, size_t ws_bytes, void *d_rows_bc,
+                     cudaStream_t st, int parts);
+void seg3_wait_before_bc(cudaEvent_t ev);
+cudaEvent_t seg3_take_bc_wait();
 bool em_streamed_available(int K, bool with_ll, bool f32, bool seg);
 int launch_em_streamed(int P, int K, const void *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, double *stats,
-                       double *ws, unsigned *err, bool compact, cudaStream_t st);
+                       double *ws, unsigned *err, unsigned long long *chk, bool compact, cudaStream_t st);
+int launch_stream_verify(const void *rows, int64_t n_rows, bool compact, unsigned long long *chk, unsigned *err, cudaStream_t st);
 int launch_loglik(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
                   double *out, void *ws, bool force_generic, cudaStream_t st);
 int launch_loglik_seg(int P, int K, const int4 *rows, int64_t n_rows, const double *theta, const double *p, double *out,
@@ -104,6 +109,6 @@ int launch_score(int K, const int32_t *g1, const int32_t *g2, const int32_t *g3,
                  const double *p, double *scores, cudaStream_t st);
 size_t loglik_ws_bytes(int P, int K);
 int launch_normalise(int P, int K, const double *stats, const int32_t *deg, double *theta, double *p,
-                     cudaStream_t st);
+                     cudaStream_t st, const unsigned long long *skip_flag = nullptr);
 
 }  // namespace tip

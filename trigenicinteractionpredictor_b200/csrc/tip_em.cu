@@ -189,7 +189,13 @@ struct ScatterMap {
 // one launch and one copy, and the kernel follows the DMA front tile by tile.  sa.compact: the rows are the 8-byte
 // host format (tip_rows_compact_host), decoded on load.  A warp that waits longer than sa.timeout_ns sets *sa.err and
 // treats every later row as padding (count 0), so a stalled host cannot hang the GPU.
+// The CUDA memory model does not promise that a kernel racing a DMA sees whole, final 8-byte words, so the kernel PROVES
+// what it consumed: every warp adds the words it accepted into sa.chk[0] (wrapping 64-bit sum), and once the copy is
+// complete stream_verify_kernel sums the buffer itself into sa.chk[1]; a difference (a torn or stale word was consumed)
+// sets the error word to 2 and a device flag that makes the M-step leave theta / p untouched - the caller then repeats the
+// iteration from the resident rows.  Detection and repair instead of trust.
 struct StreamArrive {
+    unsigned long long *chk;  // device: {consumed sum, buffer sum, blocks done, mismatch flag}
     unsigned *err;
     int compact;
     unsigned long long timeout_ns;
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(32) __maxnreg__(em_max_regs(MINB))
     // STREAM: per-lane tile index of the next fetch
     unsigned tile_v = bx_v;
     bool stream_dead = false;
-    unsigned long long dbg_spins = 0;
+    unsigned long long dbg_spins = 0, consumed = 0;
     if constexpr (STREAM) {
         if (sa.dbg != nullptr && bx_v == 0 && lane == 0) sa.dbg[0] = global_timer_ns();
     }
@@ -281,6 +287,7 @@ __global__ void __launch_bounds__(32) __maxnreg__(em_max_regs(MINB))
                 sa.dbg[2] = global_timer_ns();
                 sa.dbg[4] = dbg_spins;
             }
+            if (!stream_dead) consumed += q0 + q1;
             if (stream_dead) {
                 v = make_int4(0, 0, 0, 0);
             } else if (sa.compact) {
@@ -668,7 +675,46 @@ __global__ void __launch_bounds__(32) __maxnreg__(em_max_regs(MINB))
     }
     if constexpr (STREAM) {
         if (sa.dbg != nullptr && bx_v == 0 && lane == 0) sa.dbg[3] = global_timer_ns();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) consumed += __shfl_xor_sync(0xffffffffu, consumed, o);
+        if (lane == 0) atomicAdd(sa.chk, consumed);
     }
+}
+
+// sum of the 8-byte words of the landed buffer against what the streamed kernel consumed (see StreamArrive)
+__global__ void __launch_bounds__(256) stream_verify_kernel(const unsigned long long *__restrict__ words, int64_t n_words,
+                                                            unsigned long long *chk, unsigned *err)
+{
+    unsigned long long s = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x) s += words[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(chk + 1, s);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long done = atomicAdd(chk + 2, 1ull) + 1;
+        if (done == gridDim.x) {
+            __threadfence();
+            const unsigned long long a = atomicAdd(chk, 0ull), b = atomicAdd(chk + 1, 0ull);
+            if (a != b && *err == 0u) {       // (a timed-out step, err == 1, consumed less by construction)
+                chk[3] = 1ull;
+                *err = 2u;
+            }
+        }
+    }
+}
+
+int launch_stream_verify(const void *rows, int64_t n_rows, bool compact, unsigned long long *chk, unsigned *err, cudaStream_t st)
+{
+    const int64_t n_words = n_rows * (compact ? 1 : 2);
+    // TIP_STREAM_INJECT_FAULT (tests): pretend the kernel consumed something else, to exercise detection and repair
+    if (getenv("TIP_STREAM_INJECT_FAULT")) TIP_CHECK_CUDA(cudaMemsetAsync(chk, 0x5A, sizeof(unsigned long long), st));
+    int64_t want = (n_words + 256 * 8 - 1) / (256 * 8);
+    const int grid = (int)(want < 1 ? 1 : (want > (int64_t)sm_count() * 4 ? (int64_t)sm_count() * 4 : want));
+    stream_verify_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned long long *>(rows), n_words, chk, err);
+    TIP_CHECK_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // Z[r][g][bc] = sum_a theta[g][a] * p[a][bc][r]   (TIP_EM_GENE_SEGMENTED; 2*P*K^3 FMA per iteration in total)
@@ -1342,9 +1388,11 @@ static int launch_streamed_k(int P, const void *rows, int64_t n_rows, int64_t n_
 }
 
 int launch_em_streamed(int P, int K, const void *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, double *stats,
-                       double *ws, unsigned *err, bool compact, cudaStream_t st)
+                       double *ws, unsigned *err, unsigned long long *chk, bool compact, cudaStream_t st)
 {
     StreamArrive sa;
+    sa.chk = chk;
+    TIP_CHECK_CUDA(cudaMemsetAsync(chk, 0, 4 * sizeof(unsigned long long), st));
     sa.dbg = getenv("TIP_HOST_STREAM_DEBUG") ? reinterpret_cast<unsigned long long *>(err) + 8 : nullptr;
     sa.err = err;
     sa.compact = compact ? 1 : 0;

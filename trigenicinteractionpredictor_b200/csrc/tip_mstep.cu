@@ -3,9 +3,12 @@
 
 namespace tip {
 
+// skip_flag (optional): a device word that, when non-zero, makes the kernel leave theta / p untouched - set by the
+// verification of a streamed E-step whose statistics cannot be trusted (tip_em.cu, StreamArrive)
 __global__ void normalise_kernel(int P, int K, const double *__restrict__ stats, const int32_t *__restrict__ deg,
-                                 double *__restrict__ theta, double *__restrict__ p)
+                                 double *__restrict__ theta, double *__restrict__ p, const unsigned long long *skip_flag)
 {
+    if (skip_flag != nullptr && *skip_flag != 0ull) return;
     const int64_t nth = (int64_t)P * K;
     const int K3 = K * K * K;
     const double *S = stats + stats_off_S(P, K);
@@ -27,14 +30,15 @@ __global__ void normalise_kernel(int P, int K, const double *__restrict__ stats,
     }
 }
 
-int launch_normalise(int P, int K, const double *stats, const int32_t *deg, double *theta, double *p, cudaStream_t st)
+int launch_normalise(int P, int K, const double *stats, const int32_t *deg, double *theta, double *p, cudaStream_t st,
+                     const unsigned long long *skip_flag)
 {
     const int64_t n = (int64_t)P * K + (int64_t)K * K * K;
     const int threads = 256;
     int64_t want = (n + threads - 1) / threads;
     int grid = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
     if (grid < 1) grid = 1;
-    normalise_kernel<<<grid, threads, 0, st>>>(P, K, stats, deg, theta, p);
+    normalise_kernel<<<grid, threads, 0, st>>>(P, K, stats, deg, theta, p, skip_flag);
     TIP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

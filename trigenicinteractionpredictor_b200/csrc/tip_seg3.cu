@@ -29,6 +29,15 @@
 // launch - chunks of up to four consecutive tiles, tiles with many runs on their own, sorted by descending cost, single
 // tiles at the very end - and the single-warp CTAs draw chunk after chunk from one atomic counter (longest processing time
 // first; two draws in flight per warp).
+//
+// Overlap of the two pass launches.  A warp needs ~7 us per tile and handles only ~10 tiles per launch, so the last tiles
+// of a launch leave most SMs idle for 15-20 us (ncu: sm__cycles_active min 84k / max 134k of 140k elapsed).  Pass B + C is
+// therefore launched with the programmatic-dependent-launch attribute and pass A releases it at once
+// (griddepcontrol.launch_dependents): its CTAs move in as pass-A CTAs retire and work on the tiles whose s values are
+// there.  sbuf starts every iteration as NaN (written by seg3_prep_kernel); pass A publishes s with st.relaxed.gpu, pass
+// B + C checks the s it gathered and re-reads (ld.relaxed.gpu) the ones still NaN.  Every pass-A tile has been drawn by
+// a resident warp before the first pass-B tile can be (A's grid is one resident wave), so the wait is bounded; a wait of
+// more than ~2 s poisons the statistics with NaN instead of hanging.
 #include <stdlib.h>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -49,6 +58,17 @@ __device__ __forceinline__ void red_add_f64_nz3(double *addr, double v)
     asm volatile("{ .reg .pred p; setp.neu.f64 p, %1, 0d0000000000000000; @p red.global.add.f64 [%0], %1; }" ::"l"(addr),
                  "d"(v)
                  : "memory");
+}
+
+__device__ __forceinline__ void st_relaxed_gpu_f64(double *addr, double v)
+{
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_gpu_f64(const double *addr)
+{
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(addr) : "memory");
+    return v;
 }
 
 template <int K>
@@ -86,7 +106,7 @@ struct S3Args {
     unsigned *counter;       // schedule position counter of this launch, zero on entry
     const int *sched;        // chunks of this launch: (first tile << 3) | tiles, by descending cost; 0 = end of the list
     int n_sched;             // entries in sched (real chunks first, zeros behind them)
-    int tune;                // bit 0: gather through L1 (cp.async.ca) instead of L2 only (.cg)
+    int tune;                // bit 0: gather through L1 (cp.async.ca) instead of L2 only (.cg); bit 4: (launcher) no overlap
 };
 
 __device__ __forceinline__ void cp_async_16_ca(void *smem_dst, const void *gmem_src)
@@ -157,6 +177,7 @@ __global__ void __launch_bounds__(32, K <= 16 ? (FIRST ? 16 : 18) : 1) seg3_pass
     constexpr int KK = C::KK, NB = C::NB, NKG = C::NKG, RS = C::RS, D = NST - 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x, li = lane & 3, ri = lane >> 2;
+    if constexpr (FIRST) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // pass B + C may move in behind us
     auto stage_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * C::BUF_BYTES); };
     auto ids_of = [&](int b) { return reinterpret_cast<int4 *>(stage_of(b) + 32 * RS + 32); };
     // fragment coordinates of this lane: component i*8 + ri of an 8 x 8 block (rows/cols >= K read as zero)
@@ -198,8 +219,11 @@ __global__ void __launch_bounds__(32, K <= 16 ? (FIRST ? 16 : 18) : 1) seg3_pass
     unsigned pos2 = 0;
     int ent = 0;
     if (lane == 0) {
-        const unsigned p0 = atomicAdd(a.counter, 1u);
-        pos2 = atomicAdd(a.counter, 1u);
+        // the first two chunks of every warp are fixed (positions w and w + #warps: the heaviest tiles, which head the
+        // list, are spread one per warp, and nobody queues at the counter before doing any work); the counter starts at
+        // 2 x #warps (written by seg3_prep_kernel)
+        const unsigned p0 = blockIdx.x;
+        pos2 = blockIdx.x + gridDim.x;
         ent = p0 < (unsigned)a.n_sched ? __ldg(a.sched + p0) : 0;
     }
     auto next_tile = [&]() -> int {
@@ -284,6 +308,26 @@ __global__ void __launch_bounds__(32, K <= 16 ? (FIRST ? 16 : 18) : 1) seg3_pass
         if (cur < 0) cur = __shfl_sync(0xffffffffu, mrow, 0);
         if (lane == 0) prev = cur;
         const unsigned bm = __ballot_sync(0xffffffffu, mrow != prev);  // bit l: link l starts a new run
+
+        if constexpr (!FIRST) {
+            // s of this tile's links was gathered while pass A may still have been running: NaN = not published yet
+            const int w = ids[lane].w;
+            double sv = ssm[lane];
+            bool pending = w >= 0 && sv != sv;
+            if (__any_sync(0xffffffffu, pending)) {
+                unsigned spins = 0;
+                do {
+                    if (pending) {
+                        sv = ld_relaxed_gpu_f64(a.sbuf + w);
+                        pending = sv != sv;
+                        if (!pending) ssm[lane] = sv;
+                    }
+                    if (++spins > (1u << 23)) break;     // ~2 s: leave the NaN in place, the statistics become NaN (loud)
+                    if (pending) __nanosleep(200);
+                } while (__any_sync(0xffffffffu, pending));
+                __syncwarp();
+            }
+        }
 
         if constexpr (FIRST) {
             // ---- Y[link][b] = sum_c th_c[c] Z_g[b][c], one masked tensor product per run of equal gene ----
@@ -379,7 +423,7 @@ __global__ void __launch_bounds__(32, K <= 16 ? (FIRST ? 16 : 18) : 1) seg3_pass
             rd = rd * fma(-dsel, rd, 2.0);
             const double s = (double)row_count(ids[L].w) * rd;
             ssm[L] = s;
-            a.sbuf[(int64_t)t * 32 + L] = s;
+            st_relaxed_gpu_f64(a.sbuf + (int64_t)t * 32 + L, s);
             __syncwarp();
         }
 
@@ -458,8 +502,24 @@ __global__ void __launch_bounds__(32, K <= 16 ? (FIRST ? 16 : 18) : 1) seg3_pass
 constexpr int kPrepGenes = 16;
 __global__ void __launch_bounds__(256) seg3_prep_kernel(int P, int K, const double *__restrict__ theta,
                                                         const double *__restrict__ p, double *__restrict__ Zg,
-                                                        double *__restrict__ PT, double *__restrict__ thpad, int TP)
+                                                        double *__restrict__ PT, double *__restrict__ thpad, int TP,
+                                                        double2 *__restrict__ zero2, int64_t n_zero2,
+                                                        double2 *__restrict__ nan2, int64_t n_nan2,
+                                                        unsigned *__restrict__ cnt_a, unsigned cnt_a0,
+                                                        unsigned *__restrict__ cnt_bc, unsigned cnt_bc0)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {   // schedule positions 0 .. 2 x #warps - 1 are taken statically
+        *cnt_a = cnt_a0;
+        *cnt_bc = cnt_bc0;
+    }
+    // the accumulators M and the schedule counters start every E-step from zero, sbuf from NaN ("not published"):
+    // fire-and-forget stores spread over the CTAs instead of two memset launches
+    {
+        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t i = tid; i < n_zero2; i += nth) zero2[i] = make_double2(0.0, 0.0);
+        const double qn = __longlong_as_double(-1ll);
+        for (int64_t i = tid; i < n_nan2; i += nth) nan2[i] = make_double2(qn, qn);
+    }
     extern __shared__ double psm[];  // [2][K^3]  p[r][a][bc]  (K <= 20), then theta of this CTA's genes [kPrepGenes][K]
     const int KK = K * K, K3 = KK * K;
     const bool staged = K <= 20;
@@ -623,7 +683,7 @@ static int s3_tune()
     return v;
 }
 
-// TIP_SEG3_SKIP (bit mask, timing experiments only - results are wrong): 1 memset, 2 prep, 4 pass A, 8 pass B+C, 16 finish
+// TIP_SEG3_SKIP (bit mask, timing experiments only - results are wrong): 4 pass A, 8 pass B+C, 16 finish
 static int s3_skip()
 {
     static int v = -1;
@@ -660,8 +720,19 @@ static int s3_mark(int i, cudaStream_t st)
     return 0;
 }
 
+// TIP_SEG3_NO_OVERLAP=1: launch pass B + C without the programmatic-dependent-launch attribute (A/B comparison)
+static bool s3_no_overlap()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("TIP_SEG3_NO_OVERLAP");
+        v = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    return v != 0;
+}
+
 template <int K, bool FIRST, int NST, bool CA>
-static int s3_launch_pass_n(const S3Args &a, cudaStream_t st)
+static int s3_launch_pass_n(const S3Args &a, cudaStream_t st, int *grid_only)
 {
     using C = S3<K>;
     constexpr size_t smem = C::BUF_BYTES * NST;
@@ -678,17 +749,39 @@ static int s3_launch_pass_n(const S3Args &a, cudaStream_t st)
     const int64_t cap = (int64_t)sm_count() * blocks_per_sm;
     int grid = (int)(a.n_tiles < cap ? a.n_tiles : cap);
     if (grid < 1) grid = 1;
+    if (grid_only != nullptr) {
+        *grid_only = grid;
+        return 0;
+    }
+    if (!FIRST && !g_s3_timing && !s3_no_overlap() && !(a.tune & 16)) {
+        // pass B + C may start while pass A drains (see the header comment); it never waits for the grid dependency,
+        // only for the s values it needs
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TIP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, seg3_pass_kernel<K, FIRST, NST, CA>, a));
+        return 0;
+    }
     seg3_pass_kernel<K, FIRST, NST, CA><<<grid, 32, smem, st>>>(a);
     TIP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
+// grid_only != nullptr: only report the grid the launch would use (the prep kernel presets the schedule counters with it)
 template <int K, bool FIRST>
-static int s3_launch_pass(const S3Args &a, cudaStream_t st)
+static int s3_launch_pass(const S3Args &a, cudaStream_t st, int *grid_only = nullptr)
 {
     const bool ca = (a.tune & 1) != 0;
-    if (s3_stages(FIRST) == 1) return ca ? s3_launch_pass_n<K, FIRST, 1, true>(a, st) : s3_launch_pass_n<K, FIRST, 1, false>(a, st);
-    return ca ? s3_launch_pass_n<K, FIRST, 2, true>(a, st) : s3_launch_pass_n<K, FIRST, 2, false>(a, st);
+    if (s3_stages(FIRST) == 1)
+        return ca ? s3_launch_pass_n<K, FIRST, 1, true>(a, st, grid_only) : s3_launch_pass_n<K, FIRST, 1, false>(a, st, grid_only);
+    return ca ? s3_launch_pass_n<K, FIRST, 2, true>(a, st, grid_only) : s3_launch_pass_n<K, FIRST, 2, false>(a, st, grid_only);
 }
 
 template <int K>
@@ -698,23 +791,7 @@ static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_r
     const S3Layout l = s3_layout(P, K, n_rows);
     const int KK = K * K;
     TIP_REQUIRE(n_rows / 32 < (1ll << 27), "tip_em_step: too many tiles in one shard for the slot-segmented kernels");
-    // M and the chunk counters start from zero
     const int skip = s3_skip();
-    if (s3_mark(0, st)) return -2;
-    if (!(skip & 1)) TIP_CHECK_CUDA(cudaMemsetAsync(ws + l.off_M, 0, sizeof(double) * (l.off_cnt + kS3CounterDoubles), st));
-    else TIP_CHECK_CUDA(cudaMemsetAsync(ws + l.off_cnt, 0, sizeof(double) * kS3CounterDoubles, st));
-    if (s3_mark(1, st)) return -2;
-    if (!(skip & 2)) {
-        const size_t smem = sizeof(double) * ((K <= 20 ? 2 * KK * K : 0) + kPrepGenes * K);
-        static bool attr = false;
-        if (!attr && smem > 48 * 1024) {
-            TIP_CHECK_CUDA(cudaFuncSetAttribute(seg3_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-            attr = true;
-        }
-        seg3_prep_kernel<<<(P + kPrepGenes - 1) / kPrepGenes, 256, smem, st>>>(P, K, theta, p, ws + l.off_Z, ws + l.off_PT,
-                                                                              ws + l.off_T, S3<K>::TP);
-        TIP_CHECK_CUDA(cudaGetLastError());
-    }
     S3Args a;
     a.P = P;
     a.rows = rows;
@@ -731,17 +808,45 @@ static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_r
     const int *sched = reinterpret_cast<const int *>(rows + 3 * n_rows);   // written by tip_order_rows behind the three orders
     a.sched = sched;
     a.n_sched = a.tiles_per_order;
+    S3Args bc = a;
+    bc.rows = rows + n_rows;
+    bc.n_tiles = 2 * a.tiles_per_order;
+    bc.slot0 = 1;
+    bc.counter = reinterpret_cast<unsigned *>(ws + l.off_cnt) + kS3Groups * 32;
+    bc.sched = sched + a.tiles_per_order;
+    bc.n_sched = 2 * a.tiles_per_order;
+    int grid_a = 0, grid_bc = 0;
+    int rc = s3_launch_pass<K, true>(a, st, &grid_a);
+    if (rc) return rc;
+    rc = s3_launch_pass<K, false>(bc, st, &grid_bc);
+    if (rc) return rc;
+    // M starts every E-step from zero, sbuf from NaN ("not published"), the schedule counters behind the statically
+    // assigned positions: all written by the prep kernel (no memset launches)
+    if (s3_mark(0, st)) return -2;
+    if (s3_mark(1, st)) return -2;
+    {
+        const size_t smem = sizeof(double) * ((K <= 20 ? 2 * KK * K : 0) + kPrepGenes * K);
+        static bool attr = false;
+        if (!attr && smem > 48 * 1024) {
+            TIP_CHECK_CUDA(cudaFuncSetAttribute(seg3_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            attr = true;
+        }
+        seg3_prep_kernel<<<(P + kPrepGenes - 1) / kPrepGenes, 256, smem, st>>>(
+            P, K, theta, p, ws + l.off_Z, ws + l.off_PT, ws + l.off_T, S3<K>::TP, reinterpret_cast<double2 *>(ws + l.off_M),
+            (int64_t)l.off_cnt / 2, reinterpret_cast<double2 *>(ws + l.off_s), (n_rows < 32 ? 32 : n_rows) / 2, a.counter,
+            2u * (unsigned)grid_a, bc.counter, 2u * (unsigned)grid_bc);
+        TIP_CHECK_CUDA(cudaGetLastError());
+    }
     if (s3_mark(2, st)) return -2;
-    int rc = (skip & 4) ? 0 : s3_launch_pass<K, true>(a, st);
+    rc = (skip & 4) ? 0 : s3_launch_pass<K, true>(a, st);
     if (rc) return rc;
     if (s3_mark(3, st)) return -2;
-    a.rows = rows + n_rows;
-    a.n_tiles = 2 * a.tiles_per_order;
-    a.slot0 = 1;
-    a.counter = reinterpret_cast<unsigned *>(ws + l.off_cnt) + kS3Groups * 32;
-    a.sched = sched + a.tiles_per_order;
-    a.n_sched = 2 * a.tiles_per_order;
-    rc = (skip & 8) ? 0 : s3_launch_pass<K, false>(a, st);
+    if (cudaEvent_t ev = seg3_take_bc_wait()) {
+        // (host-buffer entry) orders b and c are still being produced on another stream
+        TIP_CHECK_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        bc.tune |= 16;   // a plain launch behind the wait (no programmatic dependency on pass A)
+    }
+    rc = (skip & 8) ? 0 : s3_launch_pass<K, false>(bc, st);
     if (rc) return rc;
     if (s3_mark(4, st)) return -2;
     if (!(skip & 16)) {
@@ -907,7 +1012,16 @@ extern "C" int tip_order_rows_workspace_bytes(int64_t n_rows, size_t *bytes)
 extern "C" int tip_order_rows(const void *d_rows, int64_t n_rows, int64_t n_rows_r0, void *d_ws, size_t ws_bytes,
                               void *d_rows_bc, void *stream)
 {
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return order_rows_parts(d_rows, n_rows, n_rows_r0, d_ws, ws_bytes, d_rows_bc, reinterpret_cast<cudaStream_t>(stream), 3);
+}
+
+namespace tip {
+// parts: 1 = the schedule of the order-a launch (needs the packed rows only), 2 = orders b and c and their schedule;
+// the host-buffer entry runs the two parts on different streams (each with its own workspace), so that pass A starts
+// while the rows are still being sorted for passes B and C
+int order_rows_parts(const void *d_rows, int64_t n_rows, int64_t n_rows_r0, void *d_ws, size_t ws_bytes, void *d_rows_bc,
+                     cudaStream_t st, int parts)
+{
     TIP_REQUIRE(n_rows >= 0 && n_rows % 32 == 0 && n_rows_r0 >= 0 && n_rows_r0 <= n_rows && n_rows < (1ll << 31),
                 "tip_order_rows: n_rows (%lld) must be a multiple of 32 below 2^31", (long long)n_rows);
     if (n_rows == 0) return 0;
@@ -922,7 +1036,7 @@ extern "C" int tip_order_rows(const void *d_rows, int64_t n_rows, int64_t n_rows
     int4 *out = reinterpret_cast<int4 *>(d_rows_bc);
     const int64_t want = (n_rows + 255) / 256;
     const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
-    for (int slot = 1; slot <= 2; ++slot) {
+    for (int slot = 1; slot <= 2 && (parts & 2); ++slot) {
         order_keys_kernel<<<grid, 256, 0, st>>>(rows, n_rows, n_rows_r0, slot, ki, vi);
         TIP_CHECK_CUDA(cudaGetLastError());
         size_t cb = cub_bytes;
@@ -934,6 +1048,7 @@ extern "C" int tip_order_rows(const void *d_rows, int64_t n_rows, int64_t n_rows
     const int T = (int)(n_rows / 32), r0 = (int)(n_rows_r0 / 32);
     int *sched = reinterpret_cast<int *>(out + 2 * n_rows);
     for (int launch = 0; launch < 2; ++launch) {
+        if (!(parts & (1 << launch))) continue;
         const int nt = launch == 0 ? T : 2 * T;
         const int n_groups = (nt + kSchedGroup - 1) / kSchedGroup, n_slots = n_groups * kSchedGroup;
         int tail_stride = n_groups / (kSchedTailTiles / kSchedGroup);
@@ -949,6 +1064,17 @@ extern "C" int tip_order_rows(const void *d_rows, int64_t n_rows, int64_t n_rows
     }
     return 0;
 }
+
+static cudaEvent_t g_s3_bc_wait = nullptr;
+// the next slot-segmented E-step waits for `ev` between pass A and pass B + C (one-shot)
+void seg3_wait_before_bc(cudaEvent_t ev) { g_s3_bc_wait = ev; }
+cudaEvent_t seg3_take_bc_wait()
+{
+    cudaEvent_t ev = g_s3_bc_wait;
+    g_s3_bc_wait = nullptr;
+    return ev;
+}
+}  // namespace tip
 
 extern "C" int64_t tip_order_rows_out_bytes(int64_t n_rows)
 {
