@@ -296,7 +296,10 @@ def run_ours(args):
                  "uniform": "uniform random triples"}
     workload = ("cfg2: 6000 genes x 1M triplets, K=10, %s, fold-1 train split = 800,000 links per GPU" % shape_txt[args.shape]
                 + ("" if world == 1 else "; %d link shards, statistics summed across ranks every iteration (%s)" % (
-                    world, "NVLink peer memory, fused into the M-step kernel" if args.exchange == "peer" else "NCCL allreduce")))
+                    world, {"peer": "pushed into the peers' inboxes over NVLink peer memory, one handshake, local sum + M-step in one kernel",
+                            "peer_rs": "reduce-scatter + M-step + all-gather in one kernel over NVLink peer memory",
+                            "peer_gather": "every rank reads every peer buffer, fused into the M-step kernel",
+                            "nccl": "NCCL allreduce"}[args.exchange])))
 
     group = torch.distributed.group.WORLD if world > 1 else None
     rng = np.random.default_rng(0)
@@ -430,7 +433,8 @@ def run_ours(args):
         line["value_" + other] = L_total / (statistics.mean(mo) * 1e-3)
         line["value_" + args.shape] = value
         line["shape_ratio_kuzmin_over_uniform"] = (line["value_kuzmin"] / line["value_uniform"])
-        del eo
+    else:
+        eo = None
 
     # ------------------------------------------------------------------ the K^3-per-link kernel and the 1e-5 mode
     if world == 1 and "k3" not in skip:
@@ -459,7 +463,10 @@ def run_ours(args):
     # ------------------------------------------------------------------ end to end through host buffers
     if "e2e" not in skip:
         line["e2e"] = _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist)
-    del eng
+        if eo is not None:
+            oth = _e2e(eo, lib, dev, group, world, theta0, pr0, L_total, args, tdist)
+            line["e2e"]["other_shape"] = {"shape": other, "value": oth["value"], "ms_per_step": oth["ms_per_step"], "variants": oth["variants"]}
+    del eng, eo
     torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------ link-shard correctness gate (N > 1)
@@ -786,8 +793,10 @@ def main():
                     help="link shape of the headline workload (BASELINE config 2 names the Kuzmin-2018 shape)")
     ap.add_argument("--skip", default="", help="comma list of legs to leave out: cfg4,cfg3,fp32,k3,e2e,cpu,dist_check")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
-                    help="N>1: how link-shard statistics are summed (NVLink peer memory fused into the M-step, or NCCL)")
+    ap.add_argument("--exchange", choices=["peer", "peer_rs", "peer_gather", "nccl"], default="peer",
+                    help="N>1: how link-shard statistics are summed over NVLink peer memory: peer = statistics pushed into the "
+                         "peers' inboxes, one handshake, local sum + M-step in one kernel; peer_rs = reduce-scatter + M-step + "
+                         "all-gather in one kernel; peer_gather = every rank reads every buffer (round 1); nccl = NCCL allreduce")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

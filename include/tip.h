@@ -97,7 +97,8 @@ int tip_pack_rows(const int32_t *d_g1, const int32_t *d_g2, const int32_t *d_g3,
  *      Behind the two orders, 3 * n_rows / 32 int32: the SCHEDULES of the two E-step launches (order a; orders b + c) -
  *      chunks of up to four consecutive 32-row tiles, (first tile << 3) | tiles, sorted by descending cost (a tile costs
  *      1 + the runs of equal gene that end in it; tiles with many runs stand alone and come first, single tiles close
- *      the list), 0-terminated.  Hub-shaped links put tiles with 20-30 one-link runs next to thousands of tiles inside
+ *      the list; bit 31 marks the last ~2400 entries, which a warp only draws when it has nothing else in hand),
+ *      0-terminated.  Hub-shaped links put tiles with 20-30 one-link runs next to thousands of tiles inside
  *      one run; the schedule is what keeps every SM busy to the end of a launch.
  *      d_rows_bc must hold tip_order_rows_out_bytes(n_rows) bytes and MUST directly follow the packed rows in memory
  *      (d_rows_bc == d_rows + n_rows rows): tip_em_step takes one pointer to all of it.
@@ -222,6 +223,28 @@ int tip_ipc_import(const void *h_handle64, int64_t offset, void **d_ptr_out);
 int tip_peer_barrier(void *const *h_flag_ptrs, void *d_epoch, int rank, int nranks, void *stream);
 int tip_normalise_peers(int P, int K, void *const *h_stats_ptrs, int nranks, const int32_t *d_deg, double *d_theta,
                         double *d_p, void *stream);
+/* The same exchange as reduce-scatter + all-gather, in ONE kernel (the default of the Python engine):
+ *   every rank signals that its statistics are complete and waits for its peers; rank r then sums slice r of the n
+ *   statistics buffers in rank order, normalises it and STORES the new theta / p values of that slice into the theta / p
+ *   arrays of every rank; the last CTA signals "delivered" and waits for the peers' signals, so that on return (in
+ *   stream order) this rank's theta and p are complete and nobody reads its statistics any more - no double buffering.
+ * Per rank and iteration 1/n of the statistics is read from each peer and 1/n of the parameters written to each.
+ * h_theta_ptrs[r] / h_p_ptrs[r]: the theta [P*K] and p [2*K^3] arrays of rank r (peer-mapped; they must live in
+ * IPC-shared memory); h_flag_ptrs[r]: 2 * nranks uint64 of rank r, zero-initialised; d_sync: three local uint64, zero.
+ * A peer that does not show up for ~10 s poisons d_sync[0] (~0) for good; the caller checks it when it synchronises. */
+int tip_peer_mstep(int P, int K, void *const *h_stats_ptrs, void *const *h_theta_ptrs, void *const *h_p_ptrs,
+                   void *const *h_flag_ptrs, void *d_sync, int rank, int nranks, const int32_t *d_deg, void *stream);
+/* Push-based exchange (the default of the Python engine): ONE kernel, ONE handshake.  Every rank stores its statistics
+ * into its slot of every peer's inbox (remote stores over NVLink), then signals; once every peer's statistics have
+ * arrived it adds the n buffers in rank order (its own statistics in place of its own slot) and runs the M-step of all
+ * of theta and p locally.  The data travels before the barrier, while slower ranks are still in their E-step, so what
+ * follows the last arrival is one flag latency and a local sum.  Replicas stay bit-identical (same numbers, same order).
+ * h_inbox_ptrs[q]: inbox of rank q FOR THIS PARITY, [nranks][n_pad] doubles (double-buffer the inboxes: iteration i uses
+ * inbox i & 1); h_flag_ptrs[q]: nranks uint64 of rank q, zero-initialised; d_sync: four local uint64, zero;
+ * n_pad: slot stride in doubles (even, >= tip_stats_len).  Timeout (~10 s) poisons d_sync[0] (~0) for good. */
+int tip_peer_push_mstep(int P, int K, const double *d_own_stats, void *const *h_inbox_ptrs, void *const *h_flag_ptrs,
+                        void *d_sync, int rank, int nranks, int64_t n_pad, const int32_t *d_deg, double *d_theta, double *d_p,
+                        void *stream);
 
 /* ---- roofline denominators: measured FMA peak of this GPU ----
  * kind 0: fp64 DFMA, 1: fp32 FFMA, 2: fp64 mma.sync (DMMA m8n8k4), 3: DFMA and DMMA interleaved.

@@ -28,13 +28,17 @@ def main(out_dir):
     theta_rk = theta if rk == 0 else mine.dirichlet(np.ones(K), size=P)
     pr_rk = pr if rk == 0 else mine.random((K, K, K, 2))
     lo, hi = tdist.shard_bounds(L, rk, w)
-    for exchange in ("nccl", "peer"):
+    for exchange in ("nccl", "peer", "peer_rs", "peer_gather"):
         eng = EMEngine(P, K, device=dev, group=torch.distributed.group.WORLD, exchange=exchange)
         eng.set_train_links(g[lo:hi, 0], g[lo:hi, 1], g[lo:hi, 2], 1 - lab[lo:hi], lab[lo:hi])   # deg is allreduced inside
         eng.set_params(theta_rk, pr_rk)
         print(rk, exchange, "links set", flush=True)
         eng.em_iterations(3, use_graph=False)            # eager, graph replays and eager again: one parity counter
-        eng.em_iterations(5, use_graph=True)
+        if rk == 1:
+            torch.cuda._sleep(int(1e8))                  # rank skew (~50 ms): the other rank must wait in the exchange,
+        eng.em_iterations(5, use_graph=True)             # not read half-written statistics (compute-sanitizer is closed here)
+        if rk == 0:
+            torch.cuda._sleep(int(6e7))
         eng.em_iteration()
         th, p = eng.get_params()
         ll = eng.loglik("train")

@@ -289,12 +289,15 @@ def test_order_rows_bit_exact(torch_cuda):
         live = ent[ent != 0]
         assert np.all(ent[len(live):] == 0), name
         seen = np.zeros(nt, dtype=np.int64)
+        flagged = [int(e) < 0 for e in live.tolist()]           # bit 31: end-game entries, the last ones of the list
+        assert flagged == sorted(flagged) and sum(flagged) <= 148 * 16
         for e in live.tolist():
+            e &= 0x7FFFFFFF
             t0, cnt = e >> 3, e & 7
             assert 1 <= cnt <= 4 and t0 + cnt <= nt
             seen[t0: t0 + cnt] += 1
         assert np.all(seen == 1), "schedule %s does not cover every tile exactly once" % name
-        first = live[0]
+        first = int(live[0]) & 0x7FFFFFFF
         assert cost[first >> 3: (first >> 3) + (first & 7)].max() == max(cost.max(), 0) or cost.max() < 7
 
 
@@ -708,6 +711,13 @@ def test_cli_writes_reference_shaped_sample_files(torch_cuda, tmp_path, capsys):
     assert main(argv[:-4] + ["-n", "1", "-o", out2, "--seed", "1000", "--mode", "segmented"]) == 0
     got2 = open(os.path.join(out2, "Sample_0_K2.csv"), encoding="utf-8").read().split("\n")
     assert float(got2[0].split("\t")[1]) == pytest.approx(float(exp[0].split("\t")[1]), rel=1e-9)
+    # --reducible: the sample file carries the gene list and goes straight through the package's own reducer
+    from trigenicinteractionpredictor_b200 import testResultsReducer as trr
+    out3 = str(tmp_path / "red") + os.sep
+    os.makedirs(out3 + "fold1")
+    assert main(argv[:-4] + ["-n", "2", "-o", out3 + "fold1" + os.sep, "--seed", "1000", "--reducible"]) == 0
+    text = open(os.path.join(out3, "fold1", "Sample_0_K2.csv"), encoding="utf-8").read()
+    assert "LIST OF REGISTERED GENES" in text and text.split("\n")[:8] == got[:8]
 
 
 def test_cfg1_full_run_matches_reference(torch_cuda, tmp_path):
@@ -809,7 +819,7 @@ def test_streamed_host_rows_many_sizes_and_repeats(torch_cuda):
     from trigenicinteractionpredictor_b200 import _cabi
     from trigenicinteractionpredictor_b200.engine import EMEngine
     lib = _cabi.load()
-    P, K = 700, 10
+    P, K = 250, 10
     for L, reps in ((300, 4), (5000, 4), (120_000, 6), (1_600_000, 6)):
         g, n0, n1, theta, pr = _random_problem(P, L, K, 1000 + L % 97)
         eng = EMEngine(P, K, flags=0)

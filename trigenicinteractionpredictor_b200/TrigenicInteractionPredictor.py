@@ -605,13 +605,15 @@ class Model:
 
 # ----------------------------------------------------------------------------------------------
 # command line: same flags, defaults, file naming, skip-if-exists and convergence rule as
-# TIP.py:1148-1279.  Additions: --seed (instead of os.getpid()), --device, --dist samples|links,
+# TIP.py:1148-1279.  Additions: --seed (instead of os.getpid()), --device, --dist samples|links, --reducible (append the
+# gene list block so that the sample files feed testResultsReducer directly),
 # --mode auto|slots|fp64|segmented|fp32 (E-step formulation: slot-segmented 4K^2 per link without per-link atomics - the
 # default for K >= 5 -, K^3 per link, gene-segmented 2K^2 per link - all the same results to rounding -, or
 # fp32-compute / fp64-accumulate within 1e-5).
 # ----------------------------------------------------------------------------------------------
-def train_sample(model, k, iterations, fcheck, bcheck, outfile=None, verbose=True, log=print):
-    """One random restart (TIP.py:1260-1279).  Returns (converged, iterations_done, checks)."""
+def train_sample(model, k, iterations, fcheck, bcheck, outfile=None, verbose=True, log=print, reducible=False):
+    """One random restart (TIP.py:1260-1279).  Returns (converged, iterations_done, checks).  reducible: append the
+    LIST OF REGISTERED GENES block (TIP.py:863-867, commented out in the reference) that testResultsReducer parses."""
     model.initialize_parameters(k)
     if verbose:
         log("Parameters have been initialized")
@@ -639,6 +641,10 @@ def train_sample(model, k, iterations, fcheck, bcheck, outfile=None, verbose=Tru
                     log("\n\t**************************\n\t* Likelihood has converged *\n\t**************************")
                 if outfile is not None:
                     model.to_file(outfile)
+                    if reducible:
+                        from .testResultsReducer import gene_list_block
+                        with codecs.open(outfile, encoding='utf-8', mode="a") as fh:
+                            fh.write(gene_list_block(model))
                 return True, it, checks
             like0 = like
     return False, it, checks
@@ -649,11 +655,11 @@ def main(argv=None):
     iterations, num_samples, sample_ini, fcheck, bcheck = 10000, 100, 0, 25, 100
     train = test = None
     outpath, argk = "", 1
-    seed, device, dist_mode, mode_flags = None, None, "none", None
+    seed, device, dist_mode, mode_flags, reducible = None, None, "none", None, False
     try:
         opts, _ = getopt.getopt(argv, "hi:n:s:f:b:o:t:e:k:",
                                 ["help", "num_iterations=", "num_samples=", "sample_ini=", "fcheck=", "bcheck=",
-                                 "out=", "train=", "test=", "k=", "seed=", "device=", "dist=", "mode="])
+                                 "out=", "train=", "test=", "k=", "seed=", "device=", "dist=", "mode=", "reducible"])
         for opt, arg in opts:
             if opt in ("-h", "--help"):
                 print(__doc__)
@@ -711,6 +717,8 @@ def main(argv=None):
                 if arg not in ("none", "samples", "links"):
                     raise ValueError
                 dist_mode = arg
+            elif opt == "--reducible":
+                reducible = True
             elif opt == "--mode":
                 if arg not in ("auto", "slots", "fp64", "segmented", "fp32"):
                     raise ValueError
@@ -758,7 +766,7 @@ def main(argv=None):
         if seed is not None:
             random.seed(seed + sample)
         write = outfile if (dist_mode != "links" or rk == 0) else None
-        train_sample(model, argk, iterations, fcheck, bcheck, outfile=write)
+        train_sample(model, argk, iterations, fcheck, bcheck, outfile=write, reducible=reducible)
     return 0
 
 

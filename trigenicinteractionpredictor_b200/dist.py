@@ -94,21 +94,35 @@ def max_over_ranks(x: float, device=None, group=None) -> float:
 
 
 class PeerExchange:
-    """Statistics exchange over NVLink peer memory (tip_peer_barrier + tip_normalise_peers) instead of an NCCL
-    allreduce.  Each rank owns one device buffer `[2][n_pad] doubles | world uint64 flags`; CUDA IPC handles are
-    swapped once through the process group, after which every rank holds a device pointer to every peer's buffer.
-    Iteration i uses statistics buffer i & 1 (double buffering makes one barrier per iteration sufficient)."""
+    """Statistics exchange over NVLink peer memory instead of an NCCL allreduce.  Each rank owns one device buffer
+    `[2][n_pad] statistics | theta [n_theta] | p [n_p] | 2 * world uint64 flags`; CUDA IPC handles are swapped once
+    through the process group, after which every rank holds a device pointer to every peer's buffer.
+      mode "push" (default): tip_peer_push_mstep - every rank stores its statistics into its slot of every peer's inbox, one
+                           handshake, local sum in rank order + M-step, one kernel; inboxes double-buffered (i & 1);
+      mode "rs":           tip_peer_mstep - reduce-scatter of the statistics, M-step of the own slice, all-gather of the
+                           new theta / p by remote stores, one kernel, two handshakes; uses statistics buffer 0 only (theta
+                           and p of the engine live INSIDE the shared buffer so that peers can write them);
+      mode "gather":       tip_peer_barrier + tip_normalise_peers - every rank reads all n buffers (round 1); iteration i
+                           uses statistics buffer i & 1 (double buffering makes one barrier per iteration sufficient)."""
 
-    def __init__(self, n_stats: int, device, group):
+    def __init__(self, n_stats: int, device, group, n_theta: int = 0, n_p: int = 0, mode: str = "push"):
         import ctypes
         from . import _cabi
         self.lib = _cabi.load()
         self.group = group
+        self.mode = mode
         self.world, self.rank = td.get_world_size(group), td.get_rank(group)
         self.n_stats = n_stats
         self.n_pad = (n_stats + 31) // 32 * 32
-        self.buf = torch.zeros(2 * self.n_pad + self.world, dtype=torch.float64, device=device)
-        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        self.n_theta, self.n_p = n_theta, n_p
+        th_pad, p_pad = (n_theta + 31) // 32 * 32, (n_p + 31) // 32 * 32
+        self.off_theta = 2 * self.n_pad
+        self.off_p = self.off_theta + th_pad
+        self.off_flags = self.off_p + p_pad
+        self.off_inbox = (self.off_flags + 2 * self.world + 31) // 32 * 32
+        n_inbox = 2 * self.world * self.n_pad if mode == "push" else 0
+        self.buf = torch.zeros(self.off_inbox + n_inbox, dtype=torch.float64, device=device)
+        self.epoch = torch.zeros(4, dtype=torch.int64, device=device)      # {epoch, CTAs done, timed out} of tip_peer_mstep
         handle = (ctypes.c_char * 64)()
         off = ctypes.c_int64(0)
         _cabi.check(self.lib.tip_ipc_export(ctypes.c_void_p(self.buf.data_ptr()), handle, ctypes.byref(off)),
@@ -127,15 +141,24 @@ class PeerExchange:
                 bases.append(out.value)
         arr = ctypes.c_void_p * self.world
         self.stats_ptrs = [arr(*[b + i * self.n_pad * 8 for b in bases]) for i in range(2)]
-        self.flag_ptrs = arr(*[b + 2 * self.n_pad * 8 for b in bases])
+        self.theta_ptrs = arr(*[b + self.off_theta * 8 for b in bases])
+        self.p_ptrs = arr(*[b + self.off_p * 8 for b in bases])
+        self.flag_ptrs = arr(*[b + self.off_flags * 8 for b in bases])
+        self.inbox_ptrs = [arr(*[b + (self.off_inbox + i * self.world * self.n_pad) * 8 for b in bases]) for i in range(2)]
         torch.cuda.synchronize(device)
         td.barrier(group=group)          # every rank has mapped every buffer before anyone signals
 
     def stats(self, parity: int) -> torch.Tensor:
         return self.buf[parity * self.n_pad: parity * self.n_pad + self.n_stats]
 
+    def theta(self) -> torch.Tensor:
+        return self.buf[self.off_theta: self.off_theta + self.n_theta]
+
+    def p(self) -> torch.Tensor:
+        return self.buf[self.off_p: self.off_p + self.n_p]
+
     def check(self):
         """Raises if a barrier timed out (a peer stopped participating)."""
-        if int(self.epoch.item()) == -1:
-            raise RuntimeError("tip_peer_barrier timed out: a peer rank stopped participating; the statistics of that "
+        if int(self.epoch[0].item()) == -1:
+            raise RuntimeError("the peer exchange timed out: a peer rank stopped participating; the statistics of that "
                                "iteration were incomplete and the parameters since then are invalid")

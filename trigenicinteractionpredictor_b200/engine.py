@@ -87,9 +87,13 @@ class EMEngine:
         # M-step kernel) or "nccl" (torch.distributed allreduce)
         self.peer = None
         self._iter = 0
-        if self.world > 1 and exchange == "peer":
+        if self.world > 1 and exchange in ("peer", "peer_rs", "peer_gather"):
             with torch.cuda.device(self.device):
-                self.peer = _dist.PeerExchange(self.n_stats, self.device, group)
+                self.peer = _dist.PeerExchange(self.n_stats, self.device, group, n_theta=self.P * self.K, n_p=2 * self.K ** 3,
+                                               mode={"peer": "push", "peer_rs": "rs", "peer_gather": "gather"}[exchange])
+                if self.peer.mode == "rs":
+                    # the peers write this rank's slice of the new parameters: theta and p live in the shared buffer
+                    self.theta, self.p = self.peer.theta(), self.peer.p()
         self.train: PackedLinks | None = None
         self.test: PackedLinks | None = None
         self.test_ids = None      # (g1, g2, g3, labels) int32 tensors in test order
@@ -212,6 +216,20 @@ class EMEngine:
             self.peer.check()
 
     def _peer_mstep(self, par):
+        if self.peer.mode == "push":
+            pe = self.peer
+            _cabi.check(self.lib.tip_peer_push_mstep(self.P, self.K, _ptr(pe.stats(par)), pe.inbox_ptrs[par], pe.flag_ptrs,
+                                                     _ptr(pe.epoch), pe.rank, pe.world, pe.n_pad, _ptr(self.train.deg),
+                                                     _ptr(self.theta), _ptr(self.p), self._stream()), "tip_peer_push_mstep")
+            self.launches += 1
+            return
+        if self.peer.mode == "rs":
+            pe = self.peer
+            _cabi.check(self.lib.tip_peer_mstep(self.P, self.K, pe.stats_ptrs[0], pe.theta_ptrs, pe.p_ptrs, pe.flag_ptrs,
+                                                _ptr(pe.epoch), pe.rank, pe.world, _ptr(self.train.deg), self._stream()),
+                        "tip_peer_mstep")
+            self.launches += 1
+            return
         _cabi.check(self.lib.tip_peer_barrier(self.peer.flag_ptrs, _ptr(self.peer.epoch), self.peer.rank,
                                               self.peer.world, self._stream()), "tip_peer_barrier")
         _cabi.check(self.lib.tip_normalise_peers(self.P, self.K, self.peer.stats_ptrs[par], self.peer.world,
@@ -266,7 +284,7 @@ class EMEngine:
     def em_iteration_host_rows(self, h_rows: torch.Tensor, compact: bool):
         """em_iteration() with the E-step reading its rows from pinned host memory."""
         if self.peer is not None:
-            par = self._iter & 1
+            par = (self._iter & 1) if self.peer.mode != "rs" else 0
             self._iter += 1
             self.em_step_host_rows(h_rows, compact, self.peer.stats(par))
             self._peer_mstep(par)
@@ -286,6 +304,8 @@ class EMEngine:
     def _iteration_body(self, par):
         """E-step, sum of statistics over link shards, M-step, on statistics buffer `par` of the peer exchange."""
         if self.peer is not None:
+            if self.peer.mode == "rs":
+                par = 0                                   # no double buffering: see tip_peer_mstep
             self.em_step(self.peer.stats(par))
             self._peer_mstep(par)
             return
@@ -307,7 +327,7 @@ class EMEngine:
             self.em_iteration()                           # warm-up outside capture (function attributes, NCCL)
             torch.cuda.synchronize(self.device)
             self._graphs, self._graph_launches = [], 0
-            for par in range(2 if self.peer is not None else 1):      # graph `par` works on statistics buffer `par`
+            for par in range(2 if (self.peer is not None and self.peer.mode != "rs") else 1):   # graph `par`: statistics buffer `par`
                 g = torch.cuda.CUDAGraph()
                 before = self.launches
                 with torch.cuda.graph(g):
@@ -361,7 +381,7 @@ class EMEngine:
         """log-likelihood by-product of the last E-step of THIS rank's rows (of the parameters that step started
         from); needs TIP_EM_WITH_LOGLIK on the K-specialised path."""
         if self.peer is not None:
-            return float(self.peer.stats((self._iter - 1) & 1)[-1].item())
+            return float(self.peer.stats(((self._iter - 1) & 1) if self.peer.mode != "rs" else 0)[-1].item())
         return float(self.stats[-1].item())
 
     @_on_device
