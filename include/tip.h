@@ -97,8 +97,7 @@ int tip_pack_rows(const int32_t *d_g1, const int32_t *d_g2, const int32_t *d_g3,
  *      Behind the two orders, 3 * n_rows / 32 int32: the SCHEDULES of the two E-step launches (order a; orders b + c) -
  *      chunks of up to four consecutive 32-row tiles, (first tile << 3) | tiles, sorted by descending cost (a tile costs
  *      1 + the runs of equal gene that end in it; tiles with many runs stand alone and come first, single tiles close
- *      the list; bit 31 marks the last ~2400 entries, which a warp only draws when it has nothing else in hand),
- *      0-terminated.  Hub-shaped links put tiles with 20-30 one-link runs next to thousands of tiles inside
+ *      the list), 0-terminated.  Hub-shaped links put tiles with 20-30 one-link runs next to thousands of tiles inside
  *      one run; the schedule is what keeps every SM busy to the end of a launch.
  *      d_rows_bc must hold tip_order_rows_out_bytes(n_rows) bytes and MUST directly follow the packed rows in memory
  *      (d_rows_bc == d_rows + n_rows rows): tip_em_step takes one pointer to all of it.

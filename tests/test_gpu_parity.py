@@ -717,7 +717,11 @@ def test_cli_writes_reference_shaped_sample_files(torch_cuda, tmp_path, capsys):
     os.makedirs(out3 + "fold1")
     assert main(argv[:-4] + ["-n", "2", "-o", out3 + "fold1" + os.sep, "--seed", "1000", "--reducible"]) == 0
     text = open(os.path.join(out3, "fold1", "Sample_0_K2.csv"), encoding="utf-8").read()
-    assert "LIST OF REGISTERED GENES" in text and text.split("\n")[:8] == got[:8]
+    lines = text.split("\n")
+    assert "LIST OF REGISTERED GENES" in text and "LIST OF LINKS BETWEEN GENE IDS" in text and lines[2:8] == got[2:8]
+    assert float(lines[0].split("\t")[1]) == pytest.approx(float(got[0].split("\t")[1]), rel=1e-9)
+    names = trr._read_gene_names(os.path.join(out3, "fold1", "Sample_0_K2.csv"))
+    assert len(names) == int(got[2].split("\t")[1])       # the reducer's parser finds every gene of the model
 
 
 def test_cfg1_full_run_matches_reference(torch_cuda, tmp_path):

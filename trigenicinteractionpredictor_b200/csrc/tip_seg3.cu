@@ -226,11 +226,10 @@ __global__ void __launch_bounds__(32, K <= 16 ? (FIRST ? 16 : 18) : 1) seg3_pass
         pos2 = blockIdx.x + gridDim.x;
         ent = p0 < (unsigned)a.n_sched ? __ldg(a.sched + p0) : 0;
     }
-    bool jit = false;   // end game (entries flagged by tip_order_rows): draw a tile only when nothing else is in hand
     auto next_tile = [&]() -> int {
         if (gen_t < gen_end) return gen_t++;
         if (gen_done) return -1;
-        int e = __shfl_sync(0xffffffffu, ent, 0);
+        const int e = __shfl_sync(0xffffffffu, ent, 0);
         if (e == 0) {
             gen_done = true;
             return -1;
@@ -239,8 +238,6 @@ __global__ void __launch_bounds__(32, K <= 16 ? (FIRST ? 16 : 18) : 1) seg3_pass
             ent = pos2 < (unsigned)a.n_sched ? __ldg(a.sched + pos2) : 0;
             pos2 = atomicAdd(a.counter, 1u);
         }
-        jit = e < 0;
-        e &= 0x7fffffff;
         gen_t = e >> 3;
         gen_end = gen_t + (e & 7);
         return gen_t++;
@@ -287,15 +284,7 @@ __global__ void __launch_bounds__(32, K <= 16 ? (FIRST ? 16 : 18) : 1) seg3_pass
                 dst[j][kg] = (xv[j] && 4 * kg + li < K) ? __ldg(Zr + xo[j] * K + 4 * kg + li) : 0.0;
     };
 
-    // The queue may hold gaps in the end game: a warp then draws its next tile only when it has nothing but the current
-    // one in hand, so that the last tiles of the launch go to whichever warp is free first instead of sitting three deep
-    // in the queues of a few (the spread between the first and the last SM to finish was ~4 tile times, 25 us of a 70 us
-    // launch); a tile drawn that way passes through the row and gather stages with nothing to overlap, about 2 us each.
-    for (;;) {
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < D + RQ; ++j) any |= tq[j] >= 0;
-        if (!any && gen_done) break;
+    while (tq[0] >= 0) {
         // ---- A: gather of the tile D ahead; B: rows of the tile D + 1 ahead ----
         {
             int gb = cb + D;
@@ -303,22 +292,12 @@ __global__ void __launch_bounds__(32, K <= 16 ? (FIRST ? 16 : 18) : 1) seg3_pass
             if (tq[D] >= 0) issue_gather(gb, meq[0]);
             cp_async_commit();
         }
-        bool ahead = false;   // a tile behind the current one is already in hand
-#pragma unroll
-        for (int j = 1; j < D + RQ; ++j) ahead |= tq[j] >= 0;
-        const int tn = (jit && ahead && gen_t >= gen_end) ? -1 : next_tile();
+        const int tn = next_tile();
 #pragma unroll
         for (int j = 0; j + 1 < RQ; ++j) meq[j] = meq[j + 1];
         if (tn >= 0) meq[RQ - 1] = a.rows[(int64_t)tn * 32 + lane];
         cp_async_wait<D>();
         __syncwarp();
-        if (tq[0] < 0) {   // a gap: nothing to compute this round
-#pragma unroll
-            for (int j = 0; j + 1 < D + RQ; ++j) tq[j] = tq[j + 1];
-            tq[D + RQ - 1] = tn;
-            if (++cb == NST) cb = 0;
-            continue;
-        }
 
         const int t = tq[0];
         double *st = stage_of(cb);
@@ -936,11 +915,10 @@ __global__ void order_emit_kernel(const int4 *__restrict__ rows, const int32_t *
 constexpr int kSchedGroup = 4;        // tiles per chunk (an entry holds the count in 3 bits)
 constexpr int kSchedHeavy = 6;        // a tile with at least this many run ends is scheduled on its own
 constexpr int kSchedTailTiles = 8 * 148 * 16;   // about this many tiles are handed out one by one at the end
-constexpr int kSchedJitEntries = 148 * 16;      // the last entries (about one per resident warp) carry the end-game flag
 
 __global__ void __launch_bounds__(128) sched_build_kernel(const int4 *__restrict__ rows, int n_tiles, int tiles_per_order,
                                                           int n_tiles_r0, int tail_stride, unsigned *__restrict__ keys,
-                                                          int *__restrict__ vals, unsigned *__restrict__ n_real)
+                                                          int *__restrict__ vals)
 {
     const int lane = threadIdx.x & 31;
     const int n_groups = (n_tiles + kSchedGroup - 1) / kSchedGroup;
@@ -969,7 +947,6 @@ __global__ void __launch_bounds__(128) sched_build_kernel(const int4 *__restrict
         }
         if (lane == 0) {
             const bool tail = (g % tail_stride) == tail_stride - 1;
-            atomicAdd(n_real, (heavy || tail) ? (unsigned)nt : 1u);
 #pragma unroll
             for (int j = 0; j < kSchedGroup; ++j) {
                 unsigned key = 0;
@@ -988,14 +965,6 @@ __global__ void __launch_bounds__(128) sched_build_kernel(const int4 *__restrict
             }
         }
     }
-}
-
-// bit 31 on the last kSchedJitEntries real entries of a sorted schedule: the end game of the pass kernel
-__global__ void sched_mark_kernel(int *__restrict__ vals, int n_slots, const unsigned *__restrict__ n_real)
-{
-    const int nr = (int)*n_real;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x)
-        if (i < nr && i >= nr - kSchedJitEntries && vals[i] != 0) vals[i] |= (int)0x80000000u;
 }
 
 static size_t order_layout(int64_t n, size_t *o_ki, size_t *o_ko, size_t *o_vi, size_t *o_vo, size_t *o_cub, size_t *cub_bytes)
@@ -1085,15 +1054,11 @@ int order_rows_parts(const void *d_rows, int64_t n_rows, int64_t n_rows_r0, void
         int tail_stride = n_groups / (kSchedTailTiles / kSchedGroup);
         if (tail_stride < 4) tail_stride = 4;
         const int want_b = (n_groups + 3) / 4;
-        unsigned *n_real = ki + (n_rows - 1);   // behind the n_slots < n_rows - 1 keys
-        TIP_CHECK_CUDA(cudaMemsetAsync(n_real, 0, sizeof(unsigned), st));
         sched_build_kernel<<<want_b < sm_count() * 16 ? want_b : sm_count() * 16, 128, 0, st>>>(
-            launch == 0 ? rows : out, nt, T, r0, tail_stride, ki, vi, n_real);
+            launch == 0 ? rows : out, nt, T, r0, tail_stride, ki, vi);
         TIP_CHECK_CUDA(cudaGetLastError());
         size_t cb = cub_bytes;
         TIP_CHECK_CUDA(cub::DeviceRadixSort::SortPairsDescending(base + o_cub, cb, ki, ko, vi, vo, n_slots, 0, 8, st));
-        sched_mark_kernel<<<(n_slots + 255) / 256 < sm_count() * 8 ? (n_slots + 255) / 256 : sm_count() * 8, 256, 0, st>>>(vo, n_slots, n_real);
-        TIP_CHECK_CUDA(cudaGetLastError());
         // the first nt sorted entries hold every real chunk (there are at most nt of them); zeros follow
         TIP_CHECK_CUDA(cudaMemcpyAsync(sched + (launch == 0 ? 0 : T), vo, sizeof(int) * (size_t)nt, cudaMemcpyDeviceToDevice, st));
     }
