@@ -598,7 +598,7 @@ def test_full_size_hub_shaped_cfg2_against_oracle(torch_cuda):
         th_o, p_o = orc.em_step_np(th_o, p_o, ids_h, cnt)
     eng = EMEngine(P, K)
     eng.set_train_links(g1, g2, g3, 1 - lab, lab)
-    assert eng.flags & 32, "slot-segmented E-step is the default for K >= 5"
+    assert eng.flags & 32, "slot-segmented E-step is the default for K >= 4"
     eng.set_params(theta, pr)
     eng.em_iteration()
     eng.em_iteration()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """BASELINE config 5: K sweep at 10M triplets on one B200 (E-step + M-step time per iteration), every E-step formulation
-that exists for the K: slot-segmented (the default for K >= 5), K^3 per link (K <= 16), gene-segmented (K = 5..32).
+that exists for the K: slot-segmented (the default for K >= 4), K^3 per link (K <= 16), gene-segmented (K = 5..32).
     python tools/k_sweep.py [links] [K,K,...] [uniform|kuzmin] > profiles/rN_k_sweep_10M.jsonl"""
 import json
 import os

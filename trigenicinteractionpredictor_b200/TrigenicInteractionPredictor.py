@@ -608,7 +608,7 @@ class Model:
 # TIP.py:1148-1279.  Additions: --seed (instead of os.getpid()), --device, --dist samples|links, --reducible (append the
 # gene list block so that the sample files feed testResultsReducer directly),
 # --mode auto|slots|fp64|segmented|fp32 (E-step formulation: slot-segmented 4K^2 per link without per-link atomics - the
-# default for K >= 5 -, K^3 per link, gene-segmented 2K^2 per link - all the same results to rounding -, or
+# default for K >= 4 -, K^3 per link, gene-segmented 2K^2 per link - all the same results to rounding -, or
 # fp32-compute / fp64-accumulate within 1e-5).
 # ----------------------------------------------------------------------------------------------
 def train_sample(model, k, iterations, fcheck, bcheck, outfile=None, verbose=True, log=print, reducible=False):

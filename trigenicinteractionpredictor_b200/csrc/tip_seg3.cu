@@ -512,24 +512,44 @@ __global__ void __launch_bounds__(256) seg3_prep_kernel(int P, int K, const doub
         *cnt_a = cnt_a0;
         *cnt_bc = cnt_bc0;
     }
-    // the accumulators M and the schedule counters start every E-step from zero, sbuf from NaN ("not published"):
-    // fire-and-forget stores spread over the CTAs instead of two memset launches
-    {
-        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-        for (int64_t i = tid; i < n_zero2; i += nth) zero2[i] = make_double2(0.0, 0.0);
-        const double qn = __longlong_as_double(-1ll);
-        for (int64_t i = tid; i < n_nan2; i += nth) nan2[i] = make_double2(qn, qn);
-    }
     extern __shared__ double psm[];  // [2][K^3]  p[r][a][bc]  (K <= 20), then theta of this CTA's genes [kPrepGenes][K]
     const int KK = K * K, K3 = KK * K;
     const bool staged = K <= 20;
     double *tsm = psm + (staged ? 2 * K3 : 0);
     const int g0 = blockIdx.x * kPrepGenes;
     const int ng = (P - g0 < kPrepGenes) ? P - g0 : kPrepGenes;
-    if (staged)
-        for (int e = threadIdx.x; e < 2 * K3; e += blockDim.x) psm[(e & 1) * K3 + (e >> 1)] = __ldg(p + e);
+    // the loads of this CTA's operands go out FIRST (eight of p per thread and its theta value: one L2 round trip instead
+    // of eight dependent ones - the staging store was the hottest line, long-scoreboard, of the first version) ...
+    constexpr int PB = 8;
+    double pv[PB];
+    const int e_th = threadIdx.x;
+    double tv = 0.0;
+    if (e_th < ng * K) tv = __ldg(theta + (int64_t)g0 * K + e_th);
+    if (staged) {
+#pragma unroll
+        for (int j = 0; j < PB; ++j) {
+            const int e = threadIdx.x + j * 256;
+            pv[j] = e < 2 * K3 ? __ldg(p + e) : 0.0;
+        }
+    }
+    // ... and travel while the fills are issued: the accumulators M start every E-step from zero, sbuf from NaN ("not
+    // published") - fire-and-forget stores spread over the CTAs instead of two memset launches
+    {
+        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t i = tid; i < n_zero2; i += nth) zero2[i] = make_double2(0.0, 0.0);
+        const double qn = __longlong_as_double(-1ll);
+        for (int64_t i = tid; i < n_nan2; i += nth) nan2[i] = make_double2(qn, qn);
+    }
+    if (staged) {
+#pragma unroll
+        for (int j = 0; j < PB; ++j) {
+            const int e = threadIdx.x + j * 256;
+            if (e < 2 * K3) psm[(e & 1) * K3 + (e >> 1)] = pv[j];
+        }
+        for (int e = threadIdx.x + PB * 256; e < 2 * K3; e += blockDim.x) psm[(e & 1) * K3 + (e >> 1)] = __ldg(p + e);
+    }
     for (int e = threadIdx.x; e < ng * K; e += blockDim.x) {
-        const double v = __ldg(theta + (int64_t)g0 * K + e);
+        const double v = e == e_th ? tv : __ldg(theta + (int64_t)g0 * K + e);
         tsm[e] = v;
         const int gi = e / K;
         thpad[(int64_t)(g0 + gi) * TP + (e - gi * K)] = v;   // the gather copy of theta: rows on 128-byte lines

@@ -50,7 +50,8 @@ class PackedLinks:
 def default_flags(K: int) -> int:
     """E-step formulation used when the caller does not choose one: the slot-segmented kernels (4K^2 FMA per
     link, no per-link atomics, indifferent to hub genes) wherever they are the fastest correct path."""
-    return _cabi.TIP_EM_SLOT_SEGMENTED if K >= 5 else _cabi.TIP_EM_DEFAULT
+    # K sweep at 1e7 links (profiles/r2_k_sweep_10M.jsonl): K = 4: 0.67 vs 1.12 ms, K = 3: 0.96 vs 0.54 ms (K^3 per link wins)
+    return _cabi.TIP_EM_SLOT_SEGMENTED if K >= 4 else _cabi.TIP_EM_DEFAULT
 
 
 class EMEngine:
