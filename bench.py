@@ -704,6 +704,8 @@ def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
                         raise RuntimeError(lib.tip_last_error())
                 else:
                     eng.train.rows.copy_(rows_h, non_blocking=True)
+                if eng.flags & _cabi.TIP_EM_SLOT_SEGMENTED:
+                    eng.reorder_rows()                # the rows are new every step: orders b, c and the schedules again
                 eng.em_iteration()
             th_h.view(-1).copy_(eng.theta, non_blocking=True)
             p_h.view(-1).copy_(eng.p, non_blocking=True)
@@ -773,6 +775,17 @@ def _e2e(eng, lib, dev, group, world, theta0, pr0, L_total, args, tdist):
     else:
         api = ("EMEngine.em_iteration_host_rows: pinned host buffers, 8-byte rows, tip_em_step_host_rows follows the DMA "
                "front (link-sharded, %s exchange)" % args.exchange)
+        if streamed and (eng.flags & _cabi.TIP_EM_SLOT_SEGMENTED):
+            # the other variant: rows land, are expanded and ordered on the device, then the slot-segmented iteration
+            th_h.copy_(torch.from_numpy(np.ascontiguousarray(theta0)))
+            p_h.copy_(torch.from_numpy(np.ascontiguousarray(pr0)))
+            dts = timed(make_step(True, False))
+            alt = {"slot_segmented_after_landing": {"value": L_total * steps / dts, "ms_per_step": 1e3 * dts / steps},
+                   "k3_following_the_dma_front": {"value": L_total * steps / dt, "ms_per_step": 1e3 * dt / steps, "streamed": True}}
+            if dts < dt:
+                dt = dts
+                api = ("pinned host buffers, 8-byte rows: copy, tip_rows_expand, tip_order_rows, then the slot-segmented iteration "
+                       "(link-sharded, %s exchange)" % args.exchange)
     if not streamed:
         api += " - NOT streamed on this box (the streamed step gave up waiting for its rows): copy, then compute"
     # bytes are whole-job like `value`: every rank copies its own shard's rows plus the replicated parameters

@@ -240,10 +240,17 @@ int tip_peer_mstep(int P, int K, void *const *h_stats_ptrs, void *const *h_theta
  * follows the last arrival is one flag latency and a local sum.  Replicas stay bit-identical (same numbers, same order).
  * h_inbox_ptrs[q]: inbox of rank q FOR THIS PARITY, [nranks][n_pad] doubles (double-buffer the inboxes: iteration i uses
  * inbox i & 1); h_flag_ptrs[q]: nranks uint64 of rank q, zero-initialised; d_sync: four local uint64, zero;
- * n_pad: slot stride in doubles (even, >= tip_stats_len).  Timeout (~10 s) poisons d_sync[0] (~0) for good. */
+ * n_pad: slot stride in doubles (even, >= tip_stats_len).  Timeout (~10 s) poisons d_sync[0] (~0) for good.
+ * theta_pushed != 0: the Ntheta part of the statistics is already in the peers' inboxes - the E-step stored it there
+ * itself (tip_em_set_push_targets) - and only the 2 K^3 + 1 doubles behind it are sent here. */
 int tip_peer_push_mstep(int P, int K, const double *d_own_stats, void *const *h_inbox_ptrs, void *const *h_flag_ptrs,
-                        void *d_sync, int rank, int nranks, int64_t n_pad, const int32_t *d_deg, double *d_theta, double *d_p,
-                        void *stream);
+                        void *d_sync, int rank, int nranks, int64_t n_pad, int theta_pushed, const int32_t *d_deg,
+                        double *d_theta, double *d_p, void *stream);
+/* Fused compute + transfer for link shards: the NEXT tip_em_step(TIP_EM_SLOT_SEGMENTED) on this thread's process stores
+ * every row of Ntheta, as its finish kernel produces it, into this rank's slot of every peer's inbox as well (remote
+ * stores over NVLink that overlap the rest of the finish), so that tip_peer_push_mstep(theta_pushed = 1) has almost nothing
+ * left to send before it signals.  One-shot: consumed by that E-step.  h_inbox_ptrs / n_pad as for tip_peer_push_mstep. */
+int tip_em_set_push_targets(void *const *h_inbox_ptrs, int rank, int nranks, int64_t n_pad);
 
 /* ---- roofline denominators: measured FMA peak of this GPU ----
  * kind 0: fp64 DFMA, 1: fp32 FFMA, 2: fp64 mma.sync (DMMA m8n8k4), 3: DFMA and DMMA interleaved.

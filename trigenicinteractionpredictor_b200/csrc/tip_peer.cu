@@ -215,9 +215,9 @@ struct PushPtrs {
 };
 
 __global__ void __launch_bounds__(256) peer_push_mstep_kernel(int P, int K, const double *__restrict__ own, PushPtrs a, int rank,
-                                                              int n, int64_t n_pad, const int32_t *__restrict__ deg,
-                                                              double *__restrict__ theta, double *__restrict__ p,
-                                                              unsigned long long *sync)
+                                                              int n, int64_t n_pad, int64_t push_from,
+                                                              const int32_t *__restrict__ deg, double *__restrict__ theta,
+                                                              double *__restrict__ p, unsigned long long *sync)
 {
     __shared__ unsigned long long e_sh;
     __shared__ int bad, last;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) peer_push_mstep_kernel(int P, int K, cons
         for (int q = 0; q < n; ++q) {
             if (q == rank) continue;
             double2 *dst = reinterpret_cast<double2 *>(a.inbox[q] + (int64_t)rank * n_pad);
-            for (int64_t i = gtid; i < n2; i += gsz) dst[i] = src[i];
+            for (int64_t i = push_from / 2 + gtid; i < n2; i += gsz) dst[i] = src[i];   // (Ntheta may already be there)
         }
     }
     // one system-scope fence per CTA, by the thread that then counts the CTA as done: the CTA barrier makes every
@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(256) peer_push_mstep_kernel(int P, int K, cons
 using namespace tip;
 
 extern "C" int tip_peer_push_mstep(int P, int K, const double *d_own_stats, void *const *h_inbox_ptrs, void *const *h_flag_ptrs,
-                                   void *d_sync, int rank, int nranks, int64_t n_pad, const int32_t *d_deg, double *d_theta,
-                                   double *d_p, void *stream)
+                                   void *d_sync, int rank, int nranks, int64_t n_pad, int theta_pushed, const int32_t *d_deg,
+                                   double *d_theta, double *d_p, void *stream)
 {
     TIP_REQUIRE(P > 0 && K >= 1 && K <= TIP_MAX_K && d_own_stats && h_inbox_ptrs && h_flag_ptrs && d_sync && d_deg && d_theta &&
                     d_p && nranks >= 1 && nranks <= kMaxPeers && rank >= 0 && rank < nranks && n_pad >= tip_stats_len(P, K) &&
@@ -323,7 +323,8 @@ extern "C" int tip_peer_push_mstep(int P, int K, const double *d_own_stats, void
     const int cap = sm_count();
     const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
     peer_push_mstep_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        P, K, d_own_stats, a, rank, nranks, n_pad, d_deg, d_theta, d_p, reinterpret_cast<unsigned long long *>(d_sync));
+        P, K, d_own_stats, a, rank, nranks, n_pad, theta_pushed ? (int64_t)P * K : 0, d_deg, d_theta, d_p,
+        reinterpret_cast<unsigned long long *>(d_sync));
     TIP_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

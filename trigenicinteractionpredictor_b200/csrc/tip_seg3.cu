@@ -581,32 +581,43 @@ __global__ void __launch_bounds__(256) seg3_prep_kernel(int P, int K, const doub
 }
 
 // Per-gene finish.  Warp tasks, both as small fp64 tensor products straight out of L2 (no shared memory):
-//   kind 1, task (group of 8 genes, slot):  Ntheta[g][k] += th_g[k] * sum_r sum_e M_slot,r,g[e] PT[slot][r][k][e]
+//   kind 1, task (group of 8 genes):  Ntheta[g][k] = th_g[k] * sum_slot sum_r sum_e M_slot,r,g[e] PT[slot][r][k][e]
 //   kind 2, task (r, block of 8 (b,c) cells, chunk of genes):  S[r][a][bc] += sum_g th_g[a] M_0,r,g[bc]
+// A kind-1 task owns its eight rows of Ntheta (all three slots, both ratings): plain stores, no atomics - and, for link
+// shards, the SAME values stored straight into this rank's slot of every peer's inbox (S3Push): the statistics travel
+// over NVLink while the rest of the finish is still computing, and the exchange kernel that follows only has the 2 K^3
+// doubles of S left to send before it signals (tip_peer_push_mstep with theta_pushed = 1).
 constexpr int kFin3Threads = 256;
 constexpr int kFin3GeneChunk = 96;  // genes per kind-2 task
+constexpr int kS3MaxPeers = 16;
+
+struct S3Push {
+    int n;                        // number of peer destinations (0: single GPU)
+    double *dst[kS3MaxPeers];     // this rank's slot in the inbox of each peer (the own rank is not listed)
+};
 
 template <int K>
 __global__ void __launch_bounds__(kFin3Threads) seg3_finish_kernel(int P, const double *__restrict__ theta,
                                                                      const double *__restrict__ PT,
-                                                                     const double *__restrict__ Mg, double *__restrict__ stats)
+                                                                     const double *__restrict__ Mg, double *__restrict__ stats,
+                                                                     const S3Push push)
 {
     constexpr int KK = K * K, K3 = KK * K, NB = (K + 7) / 8, NBC = (KK + 7) / 8;
     const int lane = threadIdx.x & 31, li = lane & 3, ri = lane >> 2;
     const int wt = blockIdx.x * (kFin3Threads / 32) + (threadIdx.x >> 5);
-    const int n_groups = (P + 7) / 8, n_kind1 = n_groups * 3;
+    const int n_groups = (P + 7) / 8, n_kind1 = n_groups;
     const int n_chunks = (P + kFin3GeneChunk - 1) / kFin3GeneChunk, n_kind2 = 2 * NBC * n_chunks;
     if (wt < n_kind1) {
-        const int slot = wt % 3, g = (wt / 3) * 8 + ri;
+        const int g = wt * 8 + ri;
         const bool gv = g < P;
         double c[NB][2];
 #pragma unroll
         for (int i = 0; i < NB; ++i) c[i][0] = c[i][1] = 0.0;
         constexpr int NE = (KK + 3) / 4;          // k-steps over the cells of M
         constexpr int EB = NE < 32 ? NE : 32;     // loads in flight per batch
-        for (int r = 0; r < 2; ++r) {
-            const double *Mrow = Mg + ((int64_t)(slot * 2 + r) * P + (gv ? g : 0)) * KK;
-            const double *Pr = PT + (int64_t)(slot * 2 + r) * K3;
+        for (int sr = 0; sr < 6; ++sr) {          // (slot, rating)
+            const double *Mrow = Mg + ((int64_t)sr * P + (gv ? g : 0)) * KK;
+            const double *Pr = PT + (int64_t)sr * K3;
             for (int eb = 0; eb < NE; eb += EB) {
                 double av[EB];
 #pragma unroll
@@ -634,7 +645,12 @@ __global__ void __launch_bounds__(kFin3Threads) seg3_finish_kernel(int P, const 
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int k = i * 8 + 2 * li + h;
-                    if (k < K) red_add_f64_nz3(stats + (int64_t)g * K + k, __ldg(theta + (int64_t)g * K + k) * c[i][h]);
+                    if (k < K) {
+                        const int64_t at = (int64_t)g * K + k;
+                        const double v = __ldg(theta + at) * c[i][h];
+                        stats[at] = v;
+                        for (int q = 0; q < push.n; ++q) push.dst[q][at] = v;
+                    }
                 }
         }
     } else if (wt < n_kind1 + n_kind2) {
@@ -804,6 +820,8 @@ static int s3_launch_pass(const S3Args &a, cudaStream_t st, int *grid_only = nul
     return ca ? s3_launch_pass_n<K, FIRST, 2, true>(a, st, grid_only) : s3_launch_pass_n<K, FIRST, 2, false>(a, st, grid_only);
 }
 
+static S3Push g_s3_push = {};
+
 template <int K>
 static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
                             double *stats, double *ws, bool gather_l1, cudaStream_t st)
@@ -871,9 +889,11 @@ static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_r
     if (s3_mark(4, st)) return -2;
     if (!(skip & 16)) {
         constexpr int NBC = (K * K + 7) / 8;
-        const int n_tasks = ((P + 7) / 8) * 3 + 2 * NBC * ((P + kFin3GeneChunk - 1) / kFin3GeneChunk);
+        const int n_tasks = (P + 7) / 8 + 2 * NBC * ((P + kFin3GeneChunk - 1) / kFin3GeneChunk);
         const int wpc = kFin3Threads / 32;
-        seg3_finish_kernel<K><<<(n_tasks + wpc - 1) / wpc, kFin3Threads, 0, st>>>(P, theta, ws + l.off_PT, ws + l.off_M, stats);
+        const S3Push push = g_s3_push;   // one-shot: set by tip_em_set_push_targets for this E-step only
+        g_s3_push.n = 0;
+        seg3_finish_kernel<K><<<(n_tasks + wpc - 1) / wpc, kFin3Threads, 0, st>>>(P, theta, ws + l.off_PT, ws + l.off_M, stats, push);
         TIP_CHECK_CUDA(cudaGetLastError());
     }
     if (s3_mark(5, st)) return -2;
@@ -1006,6 +1026,17 @@ static size_t order_layout(int64_t n, size_t *o_ki, size_t *o_ko, size_t *o_vi, 
 }  // namespace tip
 
 using namespace tip;
+
+extern "C" int tip_em_set_push_targets(void *const *h_inbox_ptrs, int rank, int nranks, int64_t n_pad)
+{
+    TIP_REQUIRE(nranks >= 1 && nranks <= kS3MaxPeers && rank >= 0 && rank < nranks && (nranks == 1 || h_inbox_ptrs != nullptr) &&
+                    n_pad >= 0,
+                "tip_em_set_push_targets: bad arguments (nranks <= %d)", kS3MaxPeers);
+    g_s3_push.n = 0;
+    for (int q = 0; q < nranks; ++q)
+        if (q != rank) g_s3_push.dst[g_s3_push.n++] = reinterpret_cast<double *>(h_inbox_ptrs[q]) + (int64_t)rank * n_pad;
+    return 0;
+}
 
 extern "C" int tip_seg3_timing(int enable)
 {

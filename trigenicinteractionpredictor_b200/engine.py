@@ -45,6 +45,7 @@ class PackedLinks:
         self.rows, self.n_rows, self.n_rows_r0, self.n_real, self.deg = rows, n_rows, n_rows_r0, n_real, deg
         self.rows3 = None     # slot-a | slot-b | slot-c orders back to back (tip_order_rows); rows is then its first third
         self.rows3_buf = None  # the buffer behind rows3: the three orders, then the tile schedules
+        self.order_ws = None   # tip_order_rows workspace, kept for reorder_rows
 
 
 def default_flags(K: int) -> int:
@@ -147,7 +148,18 @@ class EMEngine:
                                                 ctypes.c_void_p(flat.data_ptr() + n * 16), self._stream()), "tip_order_rows")
             self.launches += 10
             torch.cuda.current_stream(self.device).synchronize()
-        links.rows3, links.rows, links.rows3_buf = rows3, rows3[:n], flat
+        links.rows3, links.rows, links.rows3_buf, links.order_ws = rows3, rows3[:n], flat, ws
+
+    @_on_device
+    def reorder_rows(self):
+        """tip_order_rows again, in place and asynchronously, after new rows have been copied into `train.rows` (order a):
+        the slot-b / slot-c orders and the schedules are derived from them on the device (bench.py's link-sharded
+        end-to-end leg: the rows of every step arrive from the host)."""
+        t = self.train
+        n = t.n_rows
+        _cabi.check(self.lib.tip_order_rows(_ptr(t.rows3_buf), n, t.n_rows_r0, _ptr(t.order_ws), int(t.order_ws.numel()),
+                                            ctypes.c_void_p(t.rows3_buf.data_ptr() + n * 16), self._stream()), "tip_order_rows")
+        self.launches += 10
 
     @_on_device
     def set_train_links(self, g1, g2, g3, n0, n1, global_deg=None):
@@ -216,12 +228,13 @@ class EMEngine:
         if self.peer is not None:
             self.peer.check()
 
-    def _peer_mstep(self, par):
+    def _peer_mstep(self, par, theta_pushed=False):
         if self.peer.mode == "push":
             pe = self.peer
             _cabi.check(self.lib.tip_peer_push_mstep(self.P, self.K, _ptr(pe.stats(par)), pe.inbox_ptrs[par], pe.flag_ptrs,
-                                                     _ptr(pe.epoch), pe.rank, pe.world, pe.n_pad, _ptr(self.train.deg),
-                                                     _ptr(self.theta), _ptr(self.p), self._stream()), "tip_peer_push_mstep")
+                                                     _ptr(pe.epoch), pe.rank, pe.world, pe.n_pad, 1 if theta_pushed else 0,
+                                                     _ptr(self.train.deg), _ptr(self.theta), _ptr(self.p), self._stream()),
+                        "tip_peer_push_mstep")
             self.launches += 1
             return
         if self.peer.mode == "rs":
@@ -307,8 +320,14 @@ class EMEngine:
         if self.peer is not None:
             if self.peer.mode == "rs":
                 par = 0                                   # no double buffering: see tip_peer_mstep
+            fused = self.peer.mode == "push" and bool(self.flags & _cabi.TIP_EM_SLOT_SEGMENTED) and self.train.n_rows > 0
+            if fused:
+                # the finish kernel of this E-step stores Ntheta into the peers' inboxes as it produces it
+                pe = self.peer
+                _cabi.check(self.lib.tip_em_set_push_targets(pe.inbox_ptrs[par], pe.rank, pe.world, pe.n_pad),
+                            "tip_em_set_push_targets")
             self.em_step(self.peer.stats(par))
-            self._peer_mstep(par)
+            self._peer_mstep(par, theta_pushed=fused)
             return
         self.em_step()
         if self.world > 1:
