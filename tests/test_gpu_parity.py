@@ -886,3 +886,49 @@ def test_streamed_step_checksum_mismatch_is_detected_and_repaired(torch_cuda, mo
                                             th_h.ctypes.data, p_h.ctypes.data, 3, fl)
             assert rc == 0, lib.tip_last_error()
             assert _relerr(th_h, th_a) < 1e-10 and _relerr(p_h, p_a) < 1e-10
+
+
+def test_order_rows_by_gene_holds_the_same_runs(torch_cuda):
+    """tip_order_rows_by_gene (counting sort, not stable) against tip_order_rows (stable radix sort): every (rating, gene)
+    run holds the same links at the same place, only their order inside a run may differ; hub-shaped and uniform rows."""
+    torch = torch_cuda
+    from trigenicinteractionpredictor_b200 import _cabi, synth
+    from trigenicinteractionpredictor_b200.engine import EMEngine
+    lib = _cabi.load()
+    P = 300
+    for shape, L in (("uniform", 40_000), ("kuzmin", 40_000), ("uniform", 700)):
+        if shape == "kuzmin":
+            a, b, c, lab = synth.kuzmin_links_soa(P, L, seed=5, n_query=6)
+        else:
+            a, b, c, lab = synth.planted_links_soa(P, L, seed=5)
+        eng = EMEngine(P, 5, flags=32)
+        eng.set_train_links(a, b, c, 1 - lab, lab)
+        t = eng.train
+        n = t.n_rows
+        want = t.rows3_buf.cpu().numpy()
+        out = torch.zeros_like(t.rows3_buf)
+        out[: 4 * n].copy_(t.rows3_buf[: 4 * n])
+        ws = torch.empty_like(t.order_ws)
+        rc = lib.tip_order_rows_by_gene(out.data_ptr(), n, t.n_rows_r0, P, ws.data_ptr(), int(ws.numel()),
+                                        out.data_ptr() + n * 16, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, lib.tip_last_error()
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        for blk in (1, 2):
+            w = want[4 * n * blk: 4 * n * (blk + 1)].reshape(n, 4)
+            g = got[4 * n * blk: 4 * n * (blk + 1)].reshape(n, 4)
+            assert np.array_equal(w[:, 0], g[:, 0]), "run layout differs (%s, order %d)" % (shape, blk)
+            blockid = (np.arange(n) >= t.n_rows_r0).astype(np.int64)
+
+            def canon(x):   # rows sorted by (rating block, gene with padding last, position in order a)
+                gene = np.where(x[:, 3] < 0, 1 << 30, x[:, 0].astype(np.int64))
+                return x[np.lexsort((x[:, 3], gene, blockid))]
+            assert np.array_equal(canon(g), canon(w)) and np.array_equal(canon(w), w)
+        # and the E-step on the re-ordered rows gives the same statistics
+        g0, n0, n1, theta, pr = _random_problem(P, 640, 5, 3)
+        eng.set_params(theta, pr)
+        eng.em_step()
+        ref = eng.stats.cpu().numpy().copy()
+        t.rows3_buf.copy_(out)
+        eng.em_step()
+        np.testing.assert_allclose(eng.stats.cpu().numpy(), ref, rtol=1e-11, atol=1e-300)

@@ -36,6 +36,7 @@ SIGNATURES = {
                               c_void_p, _pi64, _pi64, c_void_p, c_void_p]),
     "tip_order_rows_workspace_bytes": (c_int, [c_int64, _psz]),
     "tip_order_rows_out_bytes": (c_int64, [c_int64]),
+    "tip_order_rows_by_gene": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "tip_order_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p, c_void_p]),
     "tip_em_workspace_bytes": (c_int, [c_int, c_int, c_int64, c_uint, _psz]),
     "tip_em_step": (c_int, [c_int, c_int, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

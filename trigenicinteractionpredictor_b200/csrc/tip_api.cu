@@ -303,9 +303,9 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
         TIP_CHECK_CUDA(cudaMemcpyAsync(g.deg, h_deg, (size_t)P * 4, cudaMemcpyHostToDevice, g.st));
         char *rows_bc = (char *)g.rows + (size_t)n_rows * 16;
         TIP_CHECK_CUDA(cudaStreamWaitEvent(g.copy, g.ev_rows, 0));
-        if ((rc = order_rows_parts(g.rows, n_rows, n_rows_r0, g.order_ws2, g.order_ws2_b, rows_bc, g.copy, 2))) return rc;
+        if ((rc = order_rows_parts(g.rows, n_rows, n_rows_r0, g.order_ws2, g.order_ws2_b, rows_bc, g.copy, 2, P))) return rc;
         TIP_CHECK_CUDA(cudaEventRecord(g.ev_ordered, g.copy));
-        if ((rc = order_rows_parts(g.rows, n_rows, n_rows_r0, g.order_ws, g.order_ws_b, rows_bc, g.st, 1))) return rc;
+        if ((rc = order_rows_parts(g.rows, n_rows, n_rows_r0, g.order_ws, g.order_ws_b, rows_bc, g.st, 1, P))) return rc;
         for (int it = 0; it < n_iter; ++it) {
             if (it == 0) seg3_wait_before_bc(g.ev_ordered);
             rc = tip_em_step(P, K, g.rows, n_rows, n_rows_r0, (const double *)g.theta, (const double *)g.p, (double *)g.stats,
@@ -403,7 +403,7 @@ extern "C" int tip_em_iterations_host(int P, int K, const void *h_rows, int64_t 
     }
     auto run_resident = [&](int first) -> int {
         if (seg3 && first < n_iter) {
-            int rc2 = tip_order_rows(g.rows, n_rows, n_rows_r0, g.order_ws, g.order_ws_b, (char *)g.rows + (size_t)n_rows * 16, g.st);
+            int rc2 = tip_order_rows_by_gene(g.rows, n_rows, n_rows_r0, P, g.order_ws, g.order_ws_b, (char *)g.rows + (size_t)n_rows * 16, g.st);
             if (rc2) return rc2;
         }
         for (int it = first; it < n_iter; ++it) {

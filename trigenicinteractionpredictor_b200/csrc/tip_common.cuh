@@ -91,7 +91,7 @@ int launch_em_seg3(int P, int K, const int4 *rows, int64_t n_rows, int64_t n_row
                    double *stats, double *ws, bool gather_l1, cudaStream_t st);
 size_t em_seg3_workspace_bytes(int P, int K, int64_t n_rows);
 int order_rows_parts(const void *d_rows, int64_t n_rows, int64_t n_rows_r0, void *d_ws, size_t ws_bytes, void *d_rows_bc,
-                     cudaStream_t st, int parts);
+                     cudaStream_t st, int parts, int P);
 void seg3_wait_before_bc(cudaEvent_t ev);
 cudaEvent_t seg3_take_bc_wait();
 bool em_streamed_available(int K, bool with_ll, bool f32, bool seg);

@@ -946,6 +946,76 @@ __global__ void order_emit_kernel(const int4 *__restrict__ rows, const int32_t *
     }
 }
 
+// ---- counting sort by (rating, gene) for callers that know P (tip_order_rows_by_gene, the host-buffer entry): the keys have
+// only 2 (P + 1) values, so a histogram in shared memory, one scan and one scatter with warp-aggregated cursors replace the
+// three-pass radix sort (15 us instead of 78 us per slot at 800 k rows).  NOT stable: the order of the links inside a
+// gene's run is whatever the cursors hand out - the statistics are sums over the run, so only their rounding moves.
+constexpr int kCountMaxBins = 12288;   // 48 KB of shared-memory counters
+
+__device__ __forceinline__ int order_bucket(const int4 &v, bool r1, int slot, int P)
+{
+    const int g = slot == 1 ? v.y : v.z;
+    return (r1 ? P + 1 : 0) + (row_count(v.w) > 0 ? g : P);
+}
+
+__global__ void __launch_bounds__(256) order_hist_kernel(const int4 *__restrict__ rows, int64_t n_rows, int64_t n_rows_r0, int slot,
+                                                         int P, int nb, unsigned *__restrict__ hist)
+{
+    extern __shared__ unsigned sh_cnt[];
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) sh_cnt[b] = 0u;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&sh_cnt[order_bucket(rows[i], i >= n_rows_r0, slot, P)], 1u);
+    __syncthreads();
+    for (int b = threadIdx.x; b < nb; b += blockDim.x)
+        if (sh_cnt[b]) atomicAdd(hist + b, sh_cnt[b]);
+}
+
+// exclusive prefix sum of nb <= kCountMaxBins counters, in place, one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) order_scan_kernel(unsigned *__restrict__ hist, int nb)
+{
+    __shared__ unsigned part[1024];
+    const int per = (nb + 1023) / 1024, lo = threadIdx.x * per, hi = (lo + per < nb) ? lo + per : nb;
+    unsigned s = 0;
+    for (int b = lo; b < hi; ++b) s += hist[b];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned v = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
+    for (int b = lo; b < hi; ++b) {
+        const unsigned c = hist[b];
+        hist[b] = run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(256) order_scatter_kernel(const int4 *__restrict__ rows, int64_t n_rows, int64_t n_rows_r0,
+                                                            int slot, int P, unsigned *__restrict__ cursor, int4 *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t n32 = (n_rows + 31) / 32 * 32;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool in = i < n_rows;
+        const int4 v = in ? rows[i] : make_int4(0, 0, 0, 0);
+        const int b = in ? order_bucket(v, i >= n_rows_r0, slot, P) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        const int leader = __ffs(peers) - 1, rank = __popc(peers & ((1u << lane) - 1u));
+        unsigned base = 0;
+        if (in && lane == leader) base = atomicAdd(cursor + b, (unsigned)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (in) {
+            int4 o = make_int4(0, 0, 0, -1);
+            if (row_count(v.w) > 0) o = slot == 1 ? make_int4(v.y, v.x, v.z, (int)i) : make_int4(v.z, v.x, v.y, (int)i);
+            out[base + rank] = o;
+        }
+    }
+}
+
 // ---- the schedule of a launch (see the header comment).  One warp per group of kSchedGroup consecutive tiles of the
 // launch's tile sequence (order a; or order b followed by order c).  A tile's cost = 1 + run ends inside it, where a run
 // ends wherever (slot, rating, gene) changes - exactly what the pass kernel compares.  Every group owns kSchedGroup
@@ -1063,7 +1133,14 @@ extern "C" int tip_order_rows_workspace_bytes(int64_t n_rows, size_t *bytes)
 extern "C" int tip_order_rows(const void *d_rows, int64_t n_rows, int64_t n_rows_r0, void *d_ws, size_t ws_bytes,
                               void *d_rows_bc, void *stream)
 {
-    return order_rows_parts(d_rows, n_rows, n_rows_r0, d_ws, ws_bytes, d_rows_bc, reinterpret_cast<cudaStream_t>(stream), 3);
+    return order_rows_parts(d_rows, n_rows, n_rows_r0, d_ws, ws_bytes, d_rows_bc, reinterpret_cast<cudaStream_t>(stream), 3, 0);
+}
+
+extern "C" int tip_order_rows_by_gene(const void *d_rows, int64_t n_rows, int64_t n_rows_r0, int P, void *d_ws, size_t ws_bytes,
+                                      void *d_rows_bc, void *stream)
+{
+    TIP_REQUIRE(P > 0, "tip_order_rows_by_gene: P must be positive");
+    return order_rows_parts(d_rows, n_rows, n_rows_r0, d_ws, ws_bytes, d_rows_bc, reinterpret_cast<cudaStream_t>(stream), 3, P);
 }
 
 namespace tip {
@@ -1071,7 +1148,7 @@ namespace tip {
 // the host-buffer entry runs the two parts on different streams (each with its own workspace), so that pass A starts
 // while the rows are still being sorted for passes B and C
 int order_rows_parts(const void *d_rows, int64_t n_rows, int64_t n_rows_r0, void *d_ws, size_t ws_bytes, void *d_rows_bc,
-                     cudaStream_t st, int parts)
+                     cudaStream_t st, int parts, int P)
 {
     TIP_REQUIRE(n_rows >= 0 && n_rows % 32 == 0 && n_rows_r0 >= 0 && n_rows_r0 <= n_rows && n_rows < (1ll << 31),
                 "tip_order_rows: n_rows (%lld) must be a multiple of 32 below 2^31", (long long)n_rows);
@@ -1087,7 +1164,25 @@ int order_rows_parts(const void *d_rows, int64_t n_rows, int64_t n_rows_r0, void
     int4 *out = reinterpret_cast<int4 *>(d_rows_bc);
     const int64_t want = (n_rows + 255) / 256;
     const int grid = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
-    for (int slot = 1; slot <= 2 && (parts & 2); ++slot) {
+    // P known and the (rating, gene) keys few enough for shared-memory counters: counting sort (not stable)
+    const int nb = 2 * (P + 1);
+    const bool counting = P > 0 && nb <= kCountMaxBins && nb <= n_rows;
+    for (int slot = 1; slot <= 2 && (parts & 2) && counting; ++slot) {
+        static bool attr = false;
+        if (!attr) {
+            TIP_CHECK_CUDA(cudaFuncSetAttribute(order_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCountMaxBins * 4));
+            attr = true;
+        }
+        TIP_CHECK_CUDA(cudaMemsetAsync(ki, 0, sizeof(unsigned) * (size_t)nb, st));
+        const int hgrid = grid < sm_count() * 2 ? grid : sm_count() * 2;
+        order_hist_kernel<<<hgrid, 256, sizeof(unsigned) * (size_t)nb, st>>>(rows, n_rows, n_rows_r0, slot, P, nb, ki);
+        TIP_CHECK_CUDA(cudaGetLastError());
+        order_scan_kernel<<<1, 1024, 0, st>>>(ki, nb);
+        TIP_CHECK_CUDA(cudaGetLastError());
+        order_scatter_kernel<<<grid, 256, 0, st>>>(rows, n_rows, n_rows_r0, slot, P, ki, out + (slot - 1) * n_rows);
+        TIP_CHECK_CUDA(cudaGetLastError());
+    }
+    for (int slot = 1; slot <= 2 && (parts & 2) && !counting; ++slot) {
         order_keys_kernel<<<grid, 256, 0, st>>>(rows, n_rows, n_rows_r0, slot, ki, vi);
         TIP_CHECK_CUDA(cudaGetLastError());
         size_t cb = cub_bytes;
