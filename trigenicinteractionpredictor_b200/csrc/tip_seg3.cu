@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(256) seg3_prep_kernel(int P, int K, const doub
 // shards, the SAME values stored straight into this rank's slot of every peer's inbox (S3Push): the statistics travel
 // over NVLink while the rest of the finish is still computing, and the exchange kernel that follows only has the 2 K^3
 // doubles of S left to send before it signals (tip_peer_push_mstep with theta_pushed = 1).
-constexpr int kFin3Threads = 256;
+constexpr int kFin3Threads = 96;    // three warps: one per slot of a gene group (kind 1), or three kind-2 tasks
 constexpr int kFin3GeneChunk = 96;  // genes per kind-2 task
 constexpr int kS3MaxPeers = 16;
 
@@ -603,21 +603,23 @@ __global__ void __launch_bounds__(kFin3Threads) seg3_finish_kernel(int P, const 
                                                                      const S3Push push)
 {
     constexpr int KK = K * K, K3 = KK * K, NB = (K + 7) / 8, NBC = (KK + 7) / 8;
-    const int lane = threadIdx.x & 31, li = lane & 3, ri = lane >> 2;
-    const int wt = blockIdx.x * (kFin3Threads / 32) + (threadIdx.x >> 5);
-    const int n_groups = (P + 7) / 8, n_kind1 = n_groups;
+    const int lane = threadIdx.x & 31, li = lane & 3, ri = lane >> 2, warp = threadIdx.x >> 5;
+    const int n_groups = (P + 7) / 8;
     const int n_chunks = (P + kFin3GeneChunk - 1) / kFin3GeneChunk, n_kind2 = 2 * NBC * n_chunks;
-    if (wt < n_kind1) {
-        const int g = wt * 8 + ri;
+    __shared__ double csm[2][NB * 2][32];
+    if ((int)blockIdx.x < n_groups) {
+        // kind 1: the CTA owns eight rows of Ntheta; warp w contracts slot w (both ratings: two batches of loads in a
+        // row, as short a dependency chain as the per-slot tasks of the first version), warp 0 adds the three and stores
+        const int slot = warp, g = blockIdx.x * 8 + ri;
         const bool gv = g < P;
         double c[NB][2];
 #pragma unroll
         for (int i = 0; i < NB; ++i) c[i][0] = c[i][1] = 0.0;
         constexpr int NE = (KK + 3) / 4;          // k-steps over the cells of M
         constexpr int EB = NE < 32 ? NE : 32;     // loads in flight per batch
-        for (int sr = 0; sr < 6; ++sr) {          // (slot, rating)
-            const double *Mrow = Mg + ((int64_t)sr * P + (gv ? g : 0)) * KK;
-            const double *Pr = PT + (int64_t)sr * K3;
+        for (int r = 0; r < 2; ++r) {
+            const double *Mrow = Mg + ((int64_t)(slot * 2 + r) * P + (gv ? g : 0)) * KK;
+            const double *Pr = PT + (int64_t)(slot * 2 + r) * K3;
             for (int eb = 0; eb < NE; eb += EB) {
                 double av[EB];
 #pragma unroll
@@ -639,7 +641,15 @@ __global__ void __launch_bounds__(kFin3Threads) seg3_finish_kernel(int P, const 
                 }
             }
         }
-        if (gv) {
+        if (warp > 0) {
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                csm[warp - 1][2 * i][lane] = c[i][0];
+                csm[warp - 1][2 * i + 1][lane] = c[i][1];
+            }
+        }
+        __syncthreads();
+        if (warp == 0 && gv) {
 #pragma unroll
             for (int i = 0; i < NB; ++i)
 #pragma unroll
@@ -647,14 +657,17 @@ __global__ void __launch_bounds__(kFin3Threads) seg3_finish_kernel(int P, const 
                     const int k = i * 8 + 2 * li + h;
                     if (k < K) {
                         const int64_t at = (int64_t)g * K + k;
-                        const double v = __ldg(theta + at) * c[i][h];
+                        const double v = __ldg(theta + at) * ((c[i][h] + csm[0][2 * i + h][lane]) + csm[1][2 * i + h][lane]);
                         stats[at] = v;
                         for (int q = 0; q < push.n; ++q) push.dst[q][at] = v;
                     }
                 }
         }
-    } else if (wt < n_kind1 + n_kind2) {
-        const int w2 = wt - n_kind1;
+        return;
+    }
+    const int wt = ((int)blockIdx.x - n_groups) * (kFin3Threads / 32) + warp;
+    if (wt < n_kind2) {
+        const int w2 = wt;
         const int chunk = w2 / (2 * NBC), rem = w2 - chunk * (2 * NBC), r = rem / NBC, bcb = rem - r * NBC;
         const int g_lo = chunk * kFin3GeneChunk, g_hi = (g_lo + kFin3GeneChunk < P) ? g_lo + kFin3GeneChunk : P;
         const int bc = bcb * 8 + ri;
@@ -889,11 +902,12 @@ static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_r
     if (s3_mark(4, st)) return -2;
     if (!(skip & 16)) {
         constexpr int NBC = (K * K + 7) / 8;
-        const int n_tasks = (P + 7) / 8 + 2 * NBC * ((P + kFin3GeneChunk - 1) / kFin3GeneChunk);
+        const int n_kind2 = 2 * NBC * ((P + kFin3GeneChunk - 1) / kFin3GeneChunk);
         const int wpc = kFin3Threads / 32;
         const S3Push push = g_s3_push;   // one-shot: set by tip_em_set_push_targets for this E-step only
         g_s3_push.n = 0;
-        seg3_finish_kernel<K><<<(n_tasks + wpc - 1) / wpc, kFin3Threads, 0, st>>>(P, theta, ws + l.off_PT, ws + l.off_M, stats, push);
+        seg3_finish_kernel<K><<<(P + 7) / 8 + (n_kind2 + wpc - 1) / wpc, kFin3Threads, 0, st>>>(P, theta, ws + l.off_PT, ws + l.off_M,
+                                                                                             stats, push);
         TIP_CHECK_CUDA(cudaGetLastError());
     }
     if (s3_mark(5, st)) return -2;
