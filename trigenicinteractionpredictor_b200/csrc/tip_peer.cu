@@ -232,25 +232,39 @@ __global__ void __launch_bounds__(256) peer_push_mstep_kernel(int P, int K, cons
     if (e == 0ull) return;                                   // poisoned by an earlier timeout
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + t, gsz = (int64_t)gridDim.x * blockDim.x;
     // ---- 1: push
-    {
+    if (push_from > 0) {
+        // Ntheta is already in the peers' inboxes (stored by the E-step's finish kernel, complete at the kernel boundary):
+        // only the 2 K^3 + 1 doubles behind it are left - CTA 0 sends them and signals, nobody counts CTAs
+        if (blockIdx.x == 0) {
+            const double2 *src = reinterpret_cast<const double2 *>(own);
+            const int64_t n2 = n_pad / 2;
+            for (int q = 0; q < n; ++q) {
+                if (q == rank) continue;
+                double2 *dst = reinterpret_cast<double2 *>(a.inbox[q] + (int64_t)rank * n_pad);
+                for (int64_t i = push_from / 2 + t; i < n2; i += blockDim.x) dst[i] = src[i];
+            }
+            __syncthreads();
+            if (t < n) st_release_sys(a.flags[t] + rank, e);   // (release = system-scope fence + store, cumulative over the CTA barrier)
+        }
+    } else {
         const double2 *src = reinterpret_cast<const double2 *>(own);
         const int64_t n2 = n_pad / 2;
         for (int q = 0; q < n; ++q) {
             if (q == rank) continue;
             double2 *dst = reinterpret_cast<double2 *>(a.inbox[q] + (int64_t)rank * n_pad);
-            for (int64_t i = push_from / 2 + gtid; i < n2; i += gsz) dst[i] = src[i];   // (Ntheta may already be there)
+            for (int64_t i = gtid; i < n2; i += gsz) dst[i] = src[i];
         }
+        // one system-scope fence per CTA, by the thread that then counts the CTA as done: the CTA barrier makes every
+        // thread's stores "observed" by thread 0, whose fence is cumulative (a fence in each of the 16k threads costs
+        // microseconds: measured, the first version of this kernel was 8 us slower than the pull formulation at n = 2)
+        __syncthreads();
+        if (t == 0) {
+            __threadfence_system();
+            last = (atomicAdd(sync + 1, 1ull) == (unsigned long long)gridDim.x - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (last && t < n) st_release_sys(a.flags[t] + rank, e);   // (release = fence + store; the counter ordered the CTAs)
     }
-    // one system-scope fence per CTA, by the thread that then counts the CTA as done: the CTA barrier makes every
-    // thread's stores "observed" by thread 0, whose fence is cumulative (a fence in each of the 16k threads costs
-    // microseconds: measured, the first version of this kernel was 8 us slower than the pull formulation at n = 2)
-    __syncthreads();
-    if (t == 0) {
-        __threadfence_system();
-        last = (atomicAdd(sync + 1, 1ull) == (unsigned long long)gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (last && t < n) st_release_sys(a.flags[t] + rank, e);   // (release = fence + store; the counter ordered the CTAs)
     // ---- 2: wait for everybody's statistics
     if (t < n) {
         const long long t0 = clock64();
