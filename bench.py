@@ -398,6 +398,10 @@ def run_ours(args):
                 "traffic": prof.get("traffic_bytes"), "traffic_source": prof.get("source", "no ncu capture in the tree"),
                 "kernel": "seg3_pass_kernel<10,...>: pass A + pass B/C launches (one E-step walks every link in three orders)",
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms / ms_per_step if world == 1 else None,
+                "kernel_share_of_serialised_estep": k_ms / sum(stage_ms),
+                "share_note": "kernel_ms and estep_stage_ms are timed with the two pass launches SERIALISED (events between them); in "
+                              "the graph-replayed step pass B + C starts while pass A drains, so kernel_ms / ms_per_step overstates "
+                              "the share; the serialised share is the one to hold against the ncu launch list",
                 "estep_stage_ms": dict(zip(["memset", "prep", "pass_a", "pass_bc", "finish"], stage_ms)),
                 "flops_per_link_update": 6 * K ** 3,
                 "accounting": "SURVEY 8d: achieved = 6 K^3 flop x links / duration of the kernel.  The kernel EXECUTES 8 K^2 flop "
