@@ -24,9 +24,18 @@ def test_reference_arm_runs_on_cpu_and_prints_one_json_line():
     assert rec["e2e"] == {"value": rec["value"], "unit": rec["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
-def test_committed_bench_line_has_the_contract_keys():
-    with open(os.path.join(ROOT, "profiles", "r1_bench_line.json")) as fh:
+import pytest
+
+
+@pytest.mark.parametrize("name", ["r1_bench_line.json", "r2_bench_line.json"])
+def test_committed_bench_line_has_the_contract_keys(name):
+    with open(os.path.join(ROOT, "profiles", name)) as fh:
         rec = json.loads(fh.read().strip().splitlines()[-1])
+    if name.startswith("r2"):
+        assert rec["cpu_baseline"]["kind"] == "reference" and rec["config"]["shape"] == "kuzmin"
+        assert rec["roofline"]["kernel_ms"] <= rec["ms_per_step"] and rec["roofline"]["binding"]["frac"] < 1.0
+        for key in ("cfg4_strong", "cfg3_samples", "value_uniform", "value_kuzmin"):
+            assert key in rec, key
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert key in rec, key
