@@ -258,11 +258,8 @@ def _links(synth, shape, P, L, seed, dev):
     return g1, g2, g3, 1 - lab, lab
 
 
-def _timed_replays(torch, eng, steps, warmup, flush_l2, dev, align=None):
-    """ms of each of `steps` graph replays (CUDA events on the launching stream), L2 flushed before every one.
-    align (N > 1): a one-element all_reduce between the flush and the start event - the 512 MB memsets of the ranks do not
-    end at the same time, and without it a step would be charged the wait for the slowest FLUSH, which no real iteration
-    loop has (there the ranks are in lockstep through the exchange of the previous iteration)."""
+def _timed_replays(torch, eng, steps, warmup, flush_l2, dev):
+    """ms of each of `steps` graph replays (CUDA events on the launching stream), L2 flushed before every one."""
     for _ in range(warmup):
         flush_l2()
         eng.graph_step()
@@ -271,8 +268,6 @@ def _timed_replays(torch, eng, steps, warmup, flush_l2, dev, align=None):
     torch.cuda.synchronize(dev)
     for i in range(steps):
         flush_l2()
-        if align is not None:
-            align()
         ev0[i].record()
         eng.graph_step()
         ev1[i].record()
@@ -317,12 +312,6 @@ def run_ours(args):
         flush.zero_()
 
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    align = None
-    if world > 1:
-        one = torch.zeros(1, dtype=torch.float32, device=dev)
-
-        def align():
-            torch.distributed.all_reduce(one, group=group)
 
     # ------------------------------------------------------------------ headline: cfg2 per GPU, default E-step
     eng = EMEngine(P, K, device=dev, group=group, exchange=args.exchange)
@@ -338,7 +327,7 @@ def run_ours(args):
         eng.graph_step()
     tdist.barrier(group)
     torch.cuda.synchronize(dev)
-    ms = _timed_replays(torch, eng, steps, 0, flush_l2, dev, align)
+    ms = _timed_replays(torch, eng, steps, 0, flush_l2, dev)
     tdist.barrier(group)
     total_ms = tdist.max_over_ranks(sum(ms), device=dev, group=group)
     ms_per_step = total_ms / steps
@@ -377,10 +366,7 @@ def run_ours(args):
         "config": {"workload": workload, "P": P, "K": K, "links_per_gpu": L_local, "links_total": L_total, "shape": args.shape,
                    "estep": "slot-segmented (TIP_EM_SLOT_SEGMENTED%s)" % (" | TIP_EM_GATHER_L1" if eng.flags & _cabi.TIP_EM_GATHER_L1 else "")
                    if seg3 else "flags %d" % eng.flags,
-                   "l2": "flushed (512 MB memset) before every timed step" + (
-                       "" if world == 1 else "; the ranks are re-aligned by a one-element all_reduce between the flush and the "
-                                             "start event of a step (the flushes do not end at the same time on all ranks)"),
-                   "cuda_graph": True},
+                   "l2": "flushed (512 MB memset) before every timed step", "cuda_graph": True},
         "value_l2_warm": L_total / (warm_ms * 1e-3),
         "gpu_launches": launches_per_step * steps,
         "clocks": clocks,
@@ -590,13 +576,7 @@ def _cfg4(rank, world, dev, group, args, theta0, pr0, flush_l2, synth, tdist):
     for _ in range(3):
         eng.graph_step()
     tdist.barrier(group)
-    align = None
-    if world > 1:
-        one = torch.zeros(1, dtype=torch.float32, device=dev)
-
-        def align():
-            torch.distributed.all_reduce(one, group=group)
-    ms = _timed_replays(torch, eng, n, 0, flush_l2, dev, align)
+    ms = _timed_replays(torch, eng, n, 0, flush_l2, dev)
     tdist.barrier(group)
     per = tdist.max_over_ranks(sum(ms), device=dev, group=group) / n
     eng._check_peer()

@@ -103,6 +103,18 @@ def load(build_if_missing: bool = True):
     if not os.path.exists(LIB_PATH):
         raise TipLibraryError("libtip.so not found at %s; run `python -m trigenicinteractionpredictor_b200.build`"
                               % LIB_PATH)
+    # a library older than the sources it sits next to must not run silently: the build writes the digest of
+    # csrc/*.cu, *.cuh and include/tip.h beside the objects; on a mismatch rebuild (nvcc is in the image), else refuse
+    try:
+        from . import build as _build
+        stamp = os.path.join(_build.OBJ_DIR, "stamp.sha256")
+        if build_if_missing and os.path.exists(stamp) and open(stamp).read().strip() != _build._digest():
+            try:
+                _build.build()
+            except Exception as exc:  # noqa: BLE001
+                raise TipLibraryError("libtip.so is older than its sources and could not be rebuilt (%s)" % exc) from exc
+    except ImportError:
+        pass
     try:
         lib = ctypes.CDLL(LIB_PATH)
     except OSError as exc:
