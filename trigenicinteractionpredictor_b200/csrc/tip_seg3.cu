@@ -177,7 +177,13 @@ __global__ void __launch_bounds__(32, K <= 16 ? (FIRST ? 16 : 18) : 1) seg3_pass
     constexpr int KK = C::KK, NB = C::NB, NKG = C::NKG, RS = C::RS, D = NST - 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x, li = lane & 3, ri = lane >> 2;
-    if constexpr (FIRST) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // pass B + C may move in behind us
+    if constexpr (FIRST) {
+        // pass A is itself a programmatic dependent of the prep kernel (its CTAs are resident and past their launch latency
+        // when the prep kernel ends): wait for the prep kernel's results FIRST, then let pass B + C move in behind us - in
+        // that order, so that pass B + C can never start before the prep kernel is complete
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     auto stage_of = [&](int b) { return reinterpret_cast<double *>(smem_raw + (size_t)b * C::BUF_BYTES); };
     auto ids_of = [&](int b) { return reinterpret_cast<int4 *>(stage_of(b) + 32 * RS + 32); };
     // fragment coordinates of this lane: component i*8 + ri of an 8 x 8 block (rows/cols >= K read as zero)
@@ -508,6 +514,7 @@ __global__ void __launch_bounds__(256) seg3_prep_kernel(int P, int K, const doub
                                                         unsigned *__restrict__ cnt_a, unsigned cnt_a0,
                                                         unsigned *__restrict__ cnt_bc, unsigned cnt_bc0)
 {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // pass A may become resident (it waits for this grid)
     if (blockIdx.x == 0 && threadIdx.x == 0) {   // schedule positions 0 .. 2 x #warps - 1 are taken statically
         *cnt_a = cnt_a0;
         *cnt_bc = cnt_bc0;
@@ -559,6 +566,21 @@ __global__ void __launch_bounds__(256) seg3_prep_kernel(int P, int K, const doub
     for (int rbc = threadIdx.x; rbc < 2 * KK; rbc += blockDim.x) {
         const int r = rbc >= KK ? 1 : 0, bc = rbc - r * KK;
         double *out = Zg + ((int64_t)r * P + g0) * KK + bc;
+        if (staged && K <= 16) {
+            // the K values of p of this cell are the same for every gene: once into registers (halves the shared-memory
+            // loads of the loop - the kernel was issue-bound on LDS + address arithmetic, ncu r2_seg3_prep_k10_final_summary)
+            double pk[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) pk[q] = q < K ? psm[r * K3 + q * KK + bc] : 0.0;
+            for (int gi = 0; gi < ng; ++gi) {
+                double z = 0.0;
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    if (q < K) z = fma(tsm[gi * K + q], pk[q], z);
+                out[(int64_t)gi * KK] = z;
+            }
+            continue;
+        }
         for (int gi = 0; gi < ng; ++gi) {
             double z = 0.0;
             if (staged)
@@ -813,9 +835,10 @@ static int s3_launch_pass_n(const S3Args &a, cudaStream_t st, int *grid_only)
         *grid_only = grid;
         return 0;
     }
-    if (!FIRST && !g_s3_timing && !s3_no_overlap() && !(a.tune & 16)) {
+    if (!g_s3_timing && !s3_no_overlap() && !(a.tune & 16)) {
         // pass B + C may start while pass A drains (see the header comment); it never waits for the grid dependency,
-        // only for the s values it needs
+        // only for the s values it needs.  Pass A is launched the same way behind the prep kernel and DOES wait
+        // (griddepcontrol.wait at its top): what it gains is its launch latency and CTA ramp
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(32);
