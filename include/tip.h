@@ -213,6 +213,21 @@ int tip_rows_compact_host(const void *h_rows, int64_t n_rows, uint64_t *h_rows8)
  * their own host->device copies (bench.py's link-sharded end-to-end leg) */
 int tip_rows_expand(const void *d_rows8, void *d_rows, int64_t n_rows, void *stream);
 
+/* ---- the digenic extension (src/TrigenicInteractionPredictor_23.py): PAIR links sharing theta, rating tensor q[K][K][2] ----
+ * d_pairs: n_pairs rows int4 {a, b, n0, n1} (gene ids in the key's string-sorted order, counts per rating; no padding,
+ * no ordering required).  For a pair: d_r = eps + sum_ij th_a[i] th_b[j] q_ij,r, s_r = n_r / d_r (_23.py:1617-1620).
+ *   tip_pairs_step       adds the pair terms of Ntheta (_23.py:1629-1630) INTO d_stats[0, P*K) - call it after tip_em_step
+ *                        (which zeroes and fills the statistics of the triplets) and before tip_normalise, with a degree
+ *                        vector that counts appearances in distinct triplets AND pairs (_23.py:1584-1586, 1615-1616) -
+ *                        and writes d_sq[2][K*K] = sum_l s_r th_a[i] th_b[j] (nqr = q * Sq, _23.py:1631)
+ *   tip_pairs_normalise  q <- nqr / (eps + nqr_0 + nqr_1), in place (_23.py:1653-1659)
+ *   tip_pairs_loglik     *d_out += sum_pairs n_r log d_r (_23.py:1551-1560; add it to tip_loglik's value) */
+int tip_pairs_step(int P, int K, const void *d_pairs, int64_t n_pairs, const double *d_theta, const double *d_q, double *d_stats,
+                   double *d_sq, void *stream);
+int tip_pairs_normalise(int K, const double *d_sq, double *d_q, void *stream);
+int tip_pairs_loglik(int P, int K, const void *d_pairs, int64_t n_pairs, const double *d_theta, const double *d_q, double *d_out,
+                     void *stream);
+
 /* ---- link shards over NVLink peer memory (replaces the NCCL allreduce between E-step and M-step) ----
  * One process per GPU.  Each rank shares its statistics buffers and a flag array with its peers:
  *   tip_ipc_export(d_ptr, handle[64], &offset)    on the owner; handle+offset travel over any host channel

@@ -932,3 +932,28 @@ def test_order_rows_by_gene_holds_the_same_runs(torch_cuda):
         t.rows3_buf.copy_(out)
         eng.em_step()
         np.testing.assert_allclose(eng.stats.cpu().numpy(), ref, rtol=1e-11, atol=1e-300)
+
+
+@pytest.mark.parametrize("flags", [None, 0, 1], ids=["default", "k3", "anyK"])
+@pytest.mark.parametrize("K", [2, 3, 10])
+def test_digenic_extension_trace_matches_the_patched_reference(torch_cuda, K, flags):
+    """SURVEY f-4: the drop-in for TrigenicInteractionPredictor_23.py (triplets + pair links with their own qr): theta, pr,
+    qr and the log-likelihood per iteration within 1e-9 of the author's code (golden from oracle/gen_golden_23.py)."""
+    import contextlib
+    import io
+    from trigenicinteractionpredictor_b200.TrigenicInteractionPredictor_23 import Model
+    case = os.path.join(GOLDEN, "digenic")
+    tr = np.load(os.path.join(case, "trace23_K%d.npz" % K))
+    m = Model(flags=flags)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.get_train_test(os.path.join(case, "train_mixed.dat"), os.path.join(case, "test_mixed.dat"))
+    random.seed(2300 + K)
+    m.initialize_parameters(K)
+    assert np.array_equal(np.array(m.qr), tr["qr0"])
+    assert m.compute_likelihood() == pytest.approx(tr["loglik"][0], rel=RTOL)
+    for it in range(len(tr["loglik"]) - 1):
+        m.make_iteration()
+        assert _relerr(m.theta, tr["theta%d" % (it + 1)]) < RTOL, "theta iteration %d" % (it + 1)
+        assert _relerr(m.pr, tr["pr%d" % (it + 1)]) < RTOL, "pr iteration %d" % (it + 1)
+        assert _relerr(m.qr, tr["qr%d" % (it + 1)]) < RTOL, "qr iteration %d" % (it + 1)
+        assert m.compute_likelihood() == pytest.approx(tr["loglik"][it + 1], rel=RTOL)

@@ -272,3 +272,50 @@ def test_oracle_against_the_live_reference_on_random_files(tmp_path, monkeypatch
     np.testing.assert_allclose(np.array(m.pr), pr, rtol=1e-12)
     assert m.compute_likelihood() == pytest.approx(orc.loglik_np(theta, pr, ids, cnt), rel=1e-12)
     assert m.compute_likelihood("test") == pytest.approx(orc.loglik_np(theta, pr, tids, tcnt), rel=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------- digenic extension (f-4)
+DIGENIC = os.path.join(GOLDEN, "digenic")
+
+
+@pytest.mark.parametrize("K", [2, 3, 10])
+def test_digenic_oracle_and_host_model_against_the_patched_reference(K):
+    """tests/golden/digenic was produced by the author's TrigenicInteractionPredictor_23.py made importable by the
+    two-token recipe of oracle/gen_golden_23.py.  The oracle restatement and the host side of the drop-in class must
+    give its ids, counts and initial parameters exactly (RNG position included) and its iterations to 1e-12."""
+    import contextlib
+    import io
+    import random
+    from oracle import digenic_oracle as dg
+    from trigenicinteractionpredictor_b200.TrigenicInteractionPredictor_23 import Model
+    tr = np.load(os.path.join(DIGENIC, "trace23_K%d.npz" % K))
+    lines = open(os.path.join(DIGENIC, "train_mixed.dat"), encoding="utf-8").read().splitlines()
+    l3, l2, P = dg.digest_mixed(lines)
+    ids3 = np.array([[int(t) for t in k.split("_")] for k in l3])
+    ids2 = np.array([[int(t) for t in k.split("_")] for k in l2])
+    cnt3, cnt2 = np.array(list(l3.values())), np.array(list(l2.values()))
+    assert P == int(tr["P"])
+    for got, want in ((ids3, "ids3"), (cnt3, "cnt3"), (ids2, "ids2"), (cnt2, "cnt2")):
+        assert np.array_equal(got, tr[want]), want
+    random.seed(2300 + K)
+    th, p, q = dg.init_params_23(P, K)
+    assert np.array_equal(th, tr["theta0"]) and np.array_equal(p, tr["pr0"]) and np.array_equal(q, tr["qr0"])
+    assert random.random() == float(tr["rng_next"])
+    assert dg.loglik_23_np(th, p, q, ids3, cnt3, ids2, cnt2) == pytest.approx(tr["loglik"][0], rel=1e-12)
+    for it in range(len(tr["loglik"]) - 1):
+        th, p, q = dg.em_step_23_np(th, p, q, ids3, cnt3, ids2, cnt2)
+        np.testing.assert_allclose(th, tr["theta%d" % (it + 1)], rtol=1e-12)
+        np.testing.assert_allclose(p, tr["pr%d" % (it + 1)], rtol=1e-12)
+        np.testing.assert_allclose(q, tr["qr%d" % (it + 1)], rtol=1e-12)
+        assert dg.loglik_23_np(th, p, q, ids3, cnt3, ids2, cnt2) == pytest.approx(tr["loglik"][it + 1], rel=1e-12)
+    # the product's host side: digestion and initialisation (no GPU needed)
+    m = Model()
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.get_train_test(os.path.join(DIGENIC, "train_mixed.dat"), os.path.join(DIGENIC, "test_mixed.dat"))
+    random.seed(2300 + K)
+    m.initialize_parameters(K)
+    a3, c3 = Model._arrays(m.links, 3)
+    a2, c2 = Model._arrays(m.dlinks, 2)
+    assert m.P == P and np.array_equal(a3, ids3) and np.array_equal(c3, cnt3) and np.array_equal(a2, ids2) and np.array_equal(c2, cnt2)
+    assert np.array_equal(np.array(m.theta), tr["theta0"]) and np.array_equal(np.array(m.pr), tr["pr0"])
+    assert np.array_equal(np.array(m.qr), tr["qr0"]) and random.random() == float(tr["rng_next"])

@@ -66,6 +66,9 @@ SIGNATURES = {
     "tip_peer_push_mstep": (c_int, [c_int, c_int, c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), c_void_p, c_int,
                                     c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tip_em_set_push_targets": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int64]),
+    "tip_pairs_step": (c_int, [c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tip_pairs_normalise": (c_int, [c_int, c_void_p, c_void_p, c_void_p]),
+    "tip_pairs_loglik": (c_int, [c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tip_measure_fma_peak": (c_int, [c_int, _pdbl]),
     "tip_measure_red_f64": (c_int, [c_int64, c_int, _pdbl]),
     "tip_measure_l2_gather": (c_int, [c_int, c_int, _pdbl]),

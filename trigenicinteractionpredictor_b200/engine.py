@@ -101,6 +101,9 @@ class EMEngine:
         self.test: PackedLinks | None = None
         self.test_ids = None      # (g1, g2, g3, labels) int32 tensors in test order
         self.em_ws = None
+        self.pairs = None         # digenic extension: int32 [n][4] rows {a, b, n0, n1}
+        self.q = None             # its rating tensor q[K][K][2] and the statistic Sq[2][K*K]
+        self.sq = None
         self._graphs = None
         self._graph_key = None
         self.launches = 0         # kernel launches issued by libtip on behalf of this engine
@@ -194,6 +197,39 @@ class EMEngine:
         g1, g2, g3, n0 = (self._as_dev_i32(x) for x in (g1, g2, g3, n0))
         labels = (n0 == 0).to(torch.int32)            # TIP.py:560-563: 0 if n0 else 1
         self.test_ids = (g1, g2, g3, labels)
+
+    @_on_device
+    def set_pair_links(self, a, b, n0, n1):
+        """Digenic extension (TrigenicInteractionPredictor_23.py): pair links that share theta.  Call after
+        set_train_links: the degree of a gene then counts its distinct triplets AND pairs (_23.py:1584-1586, 1615-1616)."""
+        if self.world > 1:
+            raise NotImplementedError("pair links are not sharded: run the digenic model in one process")
+        a, b, n0, n1 = (self._as_dev_i32(x) for x in (a, b, n0, n1))
+        self.pairs = torch.stack([a, b, n0, n1], dim=1).contiguous()
+        both = torch.cat([a, b]).to(torch.int64)
+        self.train.deg = (self.train.deg.to(torch.int64) + torch.bincount(both, minlength=self.P)[: self.P]).to(torch.int32)
+        self.q = torch.empty(2 * self.K * self.K, dtype=torch.float64, device=self.device)
+        self.sq = torch.zeros(2 * self.K * self.K, dtype=torch.float64, device=self.device)
+        self._graphs = None
+
+    @_on_device
+    def set_q(self, q):
+        qq = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64).reshape(-1))
+        assert qq.numel() == 2 * self.K * self.K
+        self.q.copy_(qq, non_blocking=False)
+
+    @_on_device
+    def get_q(self) -> np.ndarray:
+        return self.q.cpu().numpy().reshape(self.K, self.K, 2)
+
+    def _pairs_estep(self, stats):
+        _cabi.check(self.lib.tip_pairs_step(self.P, self.K, _ptr(self.pairs), int(self.pairs.shape[0]), _ptr(self.theta),
+                                            _ptr(self.q), _ptr(stats), _ptr(self.sq), self._stream()), "tip_pairs_step")
+        self.launches += 1
+
+    def _pairs_mstep(self):
+        _cabi.check(self.lib.tip_pairs_normalise(self.K, _ptr(self.sq), _ptr(self.q), self._stream()), "tip_pairs_normalise")
+        self.launches += 1
 
     @_on_device
     def degrees(self) -> np.ndarray:
@@ -332,9 +368,13 @@ class EMEngine:
             self._peer_mstep(par, theta_pushed=fused)
             return
         self.em_step()
+        if self.pairs is not None:
+            self._pairs_estep(self.stats)         # pair terms of Ntheta on top of the triplets', Sq (old theta, old q)
         if self.world > 1:
             _dist.allreduce_sum_(self.stats, self.group)
         self.normalise()
+        if self.pairs is not None:
+            self._pairs_mstep()
 
     def em_iteration(self):
         """One make_iteration.  The peer exchange double-buffers the statistics: iteration i uses buffer i & 1, and
@@ -392,6 +432,10 @@ class EMEngine:
                                         self.flags & _cabi.TIP_EM_FORCE_GENERIC, self._stream()),
                     "tip_loglik")
         self.launches += 2 if (self.K <= 10 and not (self.flags & _cabi.TIP_EM_FORCE_GENERIC)) else 1
+        if self.pairs is not None and which == "train":
+            _cabi.check(self.lib.tip_pairs_loglik(self.P, self.K, _ptr(self.pairs), int(self.pairs.shape[0]), _ptr(self.theta),
+                                                  _ptr(self.q), _ptr(self.ll_out), self._stream()), "tip_pairs_loglik")
+            self.launches += 1
         if self.world > 1 and which == "train":
             _dist.allreduce_sum_(self.ll_out, self.group)
         value = float(self.ll_out.item())
