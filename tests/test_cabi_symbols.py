@@ -72,3 +72,6 @@ def test_sass_is_sm100a_with_fp64_fma_and_cp_async():
     out = subprocess.run([cuobjdump, "-sass", _cabi.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert "DFMA" in out and "LDGSTS" in out and "REDG.E.ADD.F64" in out
+    # round 2: the slot-segmented passes run their K^2 work on the fp64 tensor path and are chained by programmatic
+    # dependent launches (griddepcontrol.wait = ACQBULK, launch_dependents = PREEXIT); the counting sort ranks with MATCH
+    assert "DMMA.8x8x4" in out and "ACQBULK" in out and "PREEXIT" in out and "MATCH.ANY" in out
