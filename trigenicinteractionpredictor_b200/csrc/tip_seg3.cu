@@ -873,6 +873,11 @@ template <int K>
 static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_rows_r0, const double *theta, const double *p,
                             double *stats, double *ws, bool gather_l1, cudaStream_t st)
 {
+    // the one-shot settings of this E-step (push targets of the finish kernel, event pass B + C has to wait for) are taken
+    // - and cleared - before anything can fail, so that an error below cannot leave them behind for a later call
+    const S3Push push = g_s3_push;
+    g_s3_push.n = 0;
+    const cudaEvent_t bc_wait = seg3_take_bc_wait();
     const S3Layout l = s3_layout(P, K, n_rows);
     const int KK = K * K;
     TIP_REQUIRE(n_rows / 32 < (1ll << 27), "tip_em_step: too many tiles in one shard for the slot-segmented kernels");
@@ -926,9 +931,9 @@ static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_r
     rc = (skip & 4) ? 0 : s3_launch_pass<K, true>(a, st);
     if (rc) return rc;
     if (s3_mark(3, st)) return -2;
-    if (cudaEvent_t ev = seg3_take_bc_wait()) {
+    if (bc_wait) {
         // (host-buffer entry) orders b and c are still being produced on another stream
-        TIP_CHECK_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        TIP_CHECK_CUDA(cudaStreamWaitEvent(st, bc_wait, 0));
         bc.tune |= 16;   // a plain launch behind the wait (no programmatic dependency on pass A)
     }
     rc = (skip & 8) ? 0 : s3_launch_pass<K, false>(bc, st);
@@ -938,8 +943,6 @@ static int launch_em_seg3_k(int P, const int4 *rows, int64_t n_rows, int64_t n_r
         constexpr int NBC = (K * K + 7) / 8;
         const int n_kind2 = 2 * NBC * ((P + kFin3GeneChunk - 1) / kFin3GeneChunk);
         const int wpc = kFin3Threads / 32;
-        const S3Push push = g_s3_push;   // one-shot: set by tip_em_set_push_targets for this E-step only
-        g_s3_push.n = 0;
         seg3_finish_kernel<K><<<(P + 7) / 8 + (n_kind2 + wpc - 1) / wpc, kFin3Threads, 0, st>>>(P, theta, ws + l.off_PT, ws + l.off_M,
                                                                                              stats, push);
         TIP_CHECK_CUDA(cudaGetLastError());
