@@ -561,7 +561,6 @@ def _dist_check(rank, world, dev, group, exchange, tdist):
 
 def _cfg4(rank, world, dev, group, args, theta0, pr0, flush_l2, synth, tdist):
     """BASELINE config 4: 6,000 genes x 1e8 triplets, K=10, link-sharded over the ranks (strong scaling)."""
-    import statistics as st
     import torch
     from trigenicinteractionpredictor_b200.engine import EMEngine
     lo, hi = tdist.shard_bounds(CFG4_LINKS, rank, world)

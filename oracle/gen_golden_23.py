@@ -18,7 +18,6 @@ import hashlib
 import io
 import os
 import random
-import re
 import sys
 import tempfile
 import contextlib
